@@ -1,0 +1,200 @@
+/*
+ * solarosc_b200.h -- C ABI of libsolarosc_b200.so
+ *
+ * B200-native (sm_100a) batched engine for the per-evaluation hot path of
+ * ALopezMoreno/DUNE_SolarOscFitter: oscillated event-rate prediction and
+ * Poisson log-likelihood for a whole batch of parameter points per call.
+ *
+ * The boundary follows the reference's only FFI precedent, the NuFast-Earth
+ * wrapper (reference src/oscillations/nuFast_wrapper.h:1-39 declares
+ * nufast_earth_create / nufast_earth_probs / nufast_earth_destroy;
+ * src/oscillations/nuFast_interface.jl:45-64,94-127 binds them with @ccall):
+ * an opaque handle created once from constant tables, evaluation calls that
+ * take caller-owned host buffers, and a destroy call.  Unlike that wrapper every
+ * call returns a status, nothing throws across the ABI, and an error string is
+ * available per handle.
+ *
+ * Which reference function each entry point stands in for:
+ *
+ *   solarosc_create        setup.jl:39-66,99-108,169-178,272-285 (tables -> LikelihoodInputs) and
+ *                          nuFast_wrapper.cpp:60-87 (handle creation)
+ *   solarosc_set_data      setup.jl:160-166,212-217 (Asimov / observed rates)
+ *   solarosc_eval_llh      total_llh, likelihood_main.jl:30-39 -> make_likelihood,
+ *                          likelihood_builder.jl:216-259 (one lnL per parameter point)
+ *   solarosc_eval_llh_grouped  the same for llhScan.jl:84-116, where the n_sys x 3 points of a
+ *                          grid cell share one oscillation stage (precomputed_osc,
+ *                          propagation_main.jl:60-66)
+ *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
+ *                          propagation_main.jl:56-157 (exclusive, non-angular branch)
+ *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
+ *   solarosc_eval_oscprobs compute_shared_osc_probs, propagation_main.jl:47-54
+ *   solarosc_eval_p1e      Osc.NumOsc.Fast.osc_prob_earth, osc.jl:448-477
+ *   solarosc_poisson_llh   poissonLogLikelihood, likelihood_statistical.jl:1-28
+ *
+ * All arithmetic is IEEE binary64.  There is no CPU fallback: every entry point
+ * needs a CUDA device of compute capability 10.0 and fails with
+ * SOLAROSC_ERR_CUDA otherwise.
+ */
+#ifndef SOLAROSC_B200_H
+#define SOLAROSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOLAROSC_ABI_VERSION 1
+#define SOLAROSC_MAX_LAYERS 8   /* Earth layers (the reference's PREM has 6) */
+#define SOLAROSC_MAX_BG 8       /* background components per channel        */
+#define SOLAROSC_N_FIXED_PARAMS 8
+
+/* status codes */
+enum {
+    SOLAROSC_OK = 0,
+    SOLAROSC_ERR_ARG = 1,      /* NULL pointer, bad size, inconsistent tables */
+    SOLAROSC_ERR_CUDA = 2,     /* no sm_100 device / CUDA runtime failure      */
+    SOLAROSC_ERR_ALLOC = 3,
+    SOLAROSC_ERR_NEGATIVE_RATE = 4 /* some point had an expected rate <= -1e-3
+                                      (the reference raises, likelihood_statistical.jl:9-14);
+                                      outputs are still written, lnL = NaN for those points */
+};
+
+/* per-point flag bits written to out_flags */
+enum {
+    SOLAROSC_FLAG_EARTH_OOB = 1u,     /* an earth_norm outside [0,2]: lnL = -Inf (likelihood_debug.jl:1-4) */
+    SOLAROSC_FLAG_NEG_WARN = 2u,      /* -1e-3 < e < 0 in some bin (reference warns)                        */
+    SOLAROSC_FLAG_NEG_ERROR = 4u,     /* e <= -1e-3 in some bin (reference errors): lnL = NaN              */
+    SOLAROSC_FLAG_NONFINITE = 8u      /* lnL is NaN for another reason                                      */
+};
+
+/*
+ * Per-detector constant tables (reference: unoscillatedSample.jl:86-116, response.jl:111-141,
+ * backgrounds.jl:53-137, setup.jl:160-178).  2-D arrays are indexed [a][b] with b fastest when
+ * solarosc_config.col_major == 0 (C / numpy) and with a fastest when col_major == 1 (Julia
+ * arrays passed as they lie in memory).
+ */
+typedef struct solarosc_detector {
+    int32_t es_mode, cc_mode;           /* det.ES_mode / det.CC_mode                                  */
+    int32_t n_ereco_es, n_ereco_cc;     /* reconstructed-energy bins per channel                      */
+    int32_t index_es, index_cc;         /* 1-based first bin entering the likelihood (setup.jl:169-178) */
+    /* unoscillated sample, each [n_etrue] */
+    const double *unosc_es_nue_8b, *unosc_es_nuother_8b, *unosc_cc_8b;
+    const double *unosc_es_nue_hep, *unosc_es_nuother_hep, *unosc_cc_hep;
+    const double *log_e_norm;
+    /* responses [n_etrue][n_ereco] (row = true-energy bin) and efficiencies [n_ereco] */
+    const double *resp_es_nue, *resp_es_nuother, *resp_cc;
+    const double *eff_es_nue, *eff_es_nuother, *eff_cc;
+    /* raw background components (propagation_bg.jl:36-83) */
+    int32_t n_bg_es, n_bg_cc;
+    const double *raw_bg_es;            /* [n_bg_es][n_ereco_es] (component-major, both layouts)      */
+    const double *raw_bg_cc;            /* [n_bg_cc][n_ereco_cc]                                      */
+    const int32_t *bg_es_sides;         /* [n_bg_es] 0 long faces, 1 end caps, else total            */
+    const int32_t *bg_es_par;           /* [n_bg_es] ES_par_counts: != 0 -> scaled by a nuisance      */
+    const int32_t *bg_cc_par;           /* [n_bg_cc] CC_par_counts                                    */
+    /* observed / Asimov data; all four may be NULL at create and supplied by solarosc_set_data */
+    const double *obs_es_day;           /* [n_ereco_es]           */
+    const double *obs_es_night;         /* [n_cosz][n_ereco_es]   */
+    const double *obs_cc_day;           /* [n_ereco_cc]           */
+    const double *obs_cc_night;         /* [n_cosz][n_ereco_cc]   */
+} solarosc_detector;
+
+/* Shared constant tables */
+typedef struct solarosc_tables {
+    int32_t n_etrue;                    /* nBins_Etrue; the oscillation grid has 2*n_etrue energies   */
+    int32_t n_cosz;                     /* coarse zenith bins                                         */
+    int32_t n_cosz_sub;                 /* N_COSZ_SUB (earthProfile.jl:165); n_paths = n_cosz*n_cosz_sub */
+    int32_t n_layers;                   /* Earth layers, <= SOLAROSC_MAX_LAYERS                       */
+    int32_t n_solar;                    /* solar-model radii (0 allowed when fast != 0)               */
+    int32_t n_det;                      /* detectors summed by total_llh                              */
+    const double *e_calc;               /* [2*n_etrue] GeV (setup.jl:39-41, propagation_osc.jl:8)     */
+    const int32_t *seg_start;           /* [n_paths+1] CSR offsets into seg_layer/seg_length          */
+    const int32_t *seg_layer;           /* [n_seg] 1-based layer id, detector -> far surface          */
+    const double *seg_length;           /* [n_seg] km                                                 */
+    const double *earth_lookup;         /* [n_layers] mean potential per layer (setup.jl:53-66)       */
+    const double *exposure_weights;     /* [n_cosz] (exposure.jl:40-43)                               */
+    double avg_ne_8b, avg_ne_hep;       /* solarModel.jl:19-20                                        */
+    const double *solar_ne, *solar_prod_8b, *solar_prod_hep; /* [n_solar] (fast == 0 only)            */
+    double cc_xsec_norm_true;           /* unused placeholder for hosts that fix the CC cross-section */
+    const solarosc_detector *det;       /* [n_det]                                                    */
+} solarosc_tables;
+
+typedef struct solarosc_config {
+    int32_t abi_version;                /* must be SOLAROSC_ABI_VERSION                               */
+    int32_t device;                     /* CUDA device ordinal                                        */
+    int32_t fast;                       /* fastFit (config.yaml:20): 1 = mean density, 0 = production-region integral */
+    int32_t earth_uncertainty;          /* earth_potential_uncertainties: 1 = earth_norm_k columns present */
+    int32_t col_major;                  /* 0 = C/numpy layout, 1 = Julia layout for 2-D inputs/outputs */
+    int32_t max_batch;                  /* points staged per internal chunk (0 = default 4096)        */
+} solarosc_config;
+
+typedef struct solarosc_handle solarosc_handle;
+
+/*
+ * Parameter matrix: params[b*P + k], P = solarosc_n_params(h), columns
+ *   0 sin2_th12  1 sin2_th13  2 dm2_21  3 integrated_8B_flux  4 integrated_HEP_flux
+ *   5 cc_xsec_norm  6 cc_xsec_tilt  7 cc_xsec_curv
+ *   then earth_norm_1..n_layers (only if earth_uncertainty),
+ *   then for each detector d: {det}_ES_bg_norm_1..nES_d, {det}_CC_bg_norm_1..nCC_d where
+ *   nES_d / nCC_d count the non-zero entries of bg_es_par / bg_cc_par (the families the reference
+ *   gathers with _params_by_prefix, core.jl:6-15).  Both channels' columns are always present,
+ *   whatever es_mode / cc_mode say.
+ */
+solarosc_handle *solarosc_create(const solarosc_tables *tables, const solarosc_config *config, int *status);
+void solarosc_destroy(solarosc_handle *h);
+const char *solarosc_last_error(const solarosc_handle *h); /* h == NULL: error of the last failed create */
+int solarosc_n_params(const solarosc_handle *h);
+int solarosc_abi_version(void);
+
+int solarosc_set_data(solarosc_handle *h, int det, const double *obs_es_day, const double *obs_es_night,
+                      const double *obs_cc_day, const double *obs_cc_night);
+
+/* lnL per point (multiply by -2 for the -2lnL of BASELINE.json); out_flags may be NULL. */
+int solarosc_eval_llh(solarosc_handle *h, const double *params, size_t n_points, double *out_lnl,
+                      uint32_t *out_flags);
+
+/* As above; points [g*group, (g+1)*group) use the oscillation columns (0..2 and earth_norm_*) of
+ * point g*group.  n_points must be a multiple of group. */
+int solarosc_eval_llh_grouped(solarosc_handle *h, const double *params, size_t n_points, size_t group,
+                              double *out_lnl, uint32_t *out_flags);
+
+/* Expected rates of detector det.  Outputs (any may be NULL), batch index slowest:
+ *   es_day [n][n_ereco_es], es_night [n][n_cosz][n_ereco_es] (col_major: [n][n_ereco_es][n_cosz]),
+ *   cc_day, cc_night likewise, bg_es [n][n_ereco_es], bg_cc [n][n_ereco_cc]. */
+int solarosc_eval_rates(solarosc_handle *h, int det, const double *params, size_t n_points, double *es_day,
+                        double *es_night, double *cc_day, double *cc_night, double *bg_es, double *bg_cc);
+
+/* Per-bin Poisson terms of detector det, shaped like the data (zeros outside idx..n-1, -Inf
+ * everywhere for a point whose earth norms are out of bounds). */
+int solarosc_eval_perbin(solarosc_handle *h, int det, const double *params, size_t n_points, double *es_day,
+                         double *es_night, double *cc_day, double *cc_night);
+
+/* nu_e survival probabilities at analysis resolution: day [n][n_etrue], night [n][n_cosz][n_etrue]
+ * (col_major: [n][n_etrue][n_cosz]); nu_other = 1 - nu_e. */
+int solarosc_eval_oscprobs(solarosc_handle *h, const double *params, size_t n_points, double *day_8b,
+                           double *night_8b, double *day_hep, double *night_hep);
+
+/* Earth-matter P(nu_1 -> nu_e) at oscillation resolution: [n][n_paths][2*n_etrue]
+ * (col_major: [n][2*n_etrue][n_paths], i.e. the reference's p1e[ip, ie]). */
+int solarosc_eval_p1e(solarosc_handle *h, const double *params, size_t n_points, double *p1e);
+
+/* Device-resident variants: d_params / d_lnl / d_flags are device pointers on the handle's device,
+ * work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream) and
+ * the call returns without synchronising. */
+int solarosc_eval_llh_device(solarosc_handle *h, const double *d_params, size_t n_points, size_t group,
+                             double *d_lnl, uint32_t *d_flags, void *stream);
+
+/* Stand-alone Poisson log-likelihood of n_vec independent (expected, measured) vector pairs of
+ * length len each, host buffers: out[v] = poissonLogLikelihood(e[v,:], m[v,:]). */
+int solarosc_poisson_llh(solarosc_handle *h, const double *expected, const double *measured, size_t n_vec,
+                         size_t len, double *out, uint32_t *out_flags);
+
+/* Device time of the kernels of the last eval call on this handle, in milliseconds (CUDA events on
+ * the launching stream): oscillation stage, rate+likelihood stage.  Returns the launch count. */
+int solarosc_last_timing(const solarosc_handle *h, float *ms_osc, float *ms_rates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLAROSC_B200_H */
