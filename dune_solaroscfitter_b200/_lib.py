@@ -1,0 +1,74 @@
+"""Loader of ``libsolarosc_b200.so`` (the C-ABI library holding the sm_100a kernels).
+
+There is no CPU or PyTorch fallback anywhere in this package: if the shared library is missing
+this raises, and if no B200 is present ``solarosc_create`` fails with ``SOLAROSC_ERR_CUDA``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from . import abi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libsolarosc_b200.so")
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh")]
+_SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
+
+EXPORTS = (
+    "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
+    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_rates",
+    "solarosc_eval_perbin", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
+    "solarosc_poisson_llh", "solarosc_last_timing",
+)
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library in-tree for sm_100a with nvcc (cross-compiles without a GPU)."""
+    stale = not os.path.exists(LIB_PATH) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _SOURCES)
+    if force or stale:
+        cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+               "-Xcompiler", "-fPIC,-O3", "-shared", "-o", LIB_PATH, _SOURCES[0], "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed building libsolarosc_b200.so")
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); "
+                           "this package has no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    dp, up, sz = C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_size_t
+    H = C.c_void_p
+    L.solarosc_abi_version.restype = C.c_int
+    L.solarosc_create.argtypes = [C.POINTER(abi.Tables), C.POINTER(abi.Config), C.POINTER(C.c_int)]
+    L.solarosc_create.restype = H
+    L.solarosc_destroy.argtypes = [H]
+    L.solarosc_destroy.restype = None
+    L.solarosc_last_error.argtypes = [H]
+    L.solarosc_last_error.restype = C.c_char_p
+    L.solarosc_n_params.argtypes = [H]
+    L.solarosc_set_data.argtypes = [H, C.c_int, dp, dp, dp, dp]
+    L.solarosc_eval_llh.argtypes = [H, dp, sz, dp, up]
+    L.solarosc_eval_llh_grouped.argtypes = [H, dp, sz, sz, dp, up]
+    L.solarosc_eval_rates.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp, dp, dp]
+    L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
+    L.solarosc_eval_oscprobs.argtypes = [H, dp, sz, dp, dp, dp, dp]
+    L.solarosc_eval_p1e.argtypes = [H, dp, sz, dp]
+    L.solarosc_eval_llh_device.argtypes = [H, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.solarosc_poisson_llh.argtypes = [H, dp, dp, sz, sz, dp, up]
+    L.solarosc_last_timing.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _lib = L
+    return L

@@ -89,7 +89,9 @@ class PackedTables:
 
     def __init__(self, shared: Mapping[str, Any], detectors: Optional[Sequence[Mapping[str, Any]]] = None,
                  data: Optional[Sequence[Optional[Mapping[str, Any]]]] = None,
-                 es_mode: bool = True, cc_mode: bool = True):
+                 es_mode: bool = True, cc_mode: bool = True, col_major: bool = False):
+        # col_major: 2-D arrays are numpy views of Julia memory, i.e. their shapes are reversed
+        # ((n_ereco, n_etrue) for a response matrix, (n_ereco, n_cosz) for night data)
         if detectors is None:
             detectors = [shared]
         self._keep: List[np.ndarray] = []
@@ -105,8 +107,9 @@ class PackedTables:
                 a = _f64(src[name]); k.append(a); setattr(ds, name, _ptr(a, _dp))
             for name in _DET_I32:
                 a = _i32(src[name]); k.append(a); setattr(ds, name, _ptr(a, _ip))
-            ds.n_ereco_es = int(np.shape(src["resp_es_nue"])[1])
-            ds.n_ereco_cc = int(np.shape(src["resp_cc"])[1])
+            ax = 0 if col_major else 1
+            ds.n_ereco_es = int(np.shape(src["resp_es_nue"])[ax])
+            ds.n_ereco_cc = int(np.shape(src["resp_cc"])[ax])
             ds.index_es, ds.index_cc = int(src["index_es"]), int(src["index_cc"])
             ds.n_bg_es, ds.n_bg_cc = int(np.shape(src["raw_bg_es"])[0]), int(np.shape(src["raw_bg_cc"])[0])
             obs = None if data is None else data[d]

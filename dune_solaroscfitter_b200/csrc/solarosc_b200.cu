@@ -1,0 +1,606 @@
+// solarosc_b200.cu -- host side of the C ABI declared in include/solarosc_b200.h.
+//
+// Owns device copies of the constant tables, a stream, pinned staging buffers and the
+// oscillation-probability workspace; every eval call stages the caller's host parameter block in
+// chunks, launches osc_kernel then rates_kernel per chunk and copies the results back.
+// There is deliberately no CPU fallback: without an sm_100 device create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "solarosc_kernels.cuh"
+
+using namespace solarosc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaFail {
+    std::string msg;
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            char buf_[512];                                                                                   \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            throw CudaFail{buf_};                                                                             \
+        }                                                                                                     \
+    } while (0)
+
+struct ArgFail {
+    std::string msg;
+};
+#define REQUIRE(cond, text)            \
+    do {                               \
+        if (!(cond)) throw ArgFail{text}; \
+    } while (0)
+
+}  // namespace
+
+struct solarosc_handle {
+    solarosc_config cfg{};
+    DevTables T{};
+    int device = 0, sm_count = 148, chunk = 4096, P = 0;
+    int max_ereco = 0;
+    int n_es[kMaxDet]{}, n_cc[kMaxDet]{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3]{};
+    std::vector<void*> dev_allocs;
+    // per-detector data buffers (device, [1+n_cosz][n_ereco]) kept so set_data can overwrite them
+    double *d_obs_es[kMaxDet]{}, *d_obs_cc[kMaxDet]{}, *d_log_es[kMaxDet]{}, *d_log_cc[kMaxDet]{};
+    bool has_data[kMaxDet]{};
+    // workspaces
+    double* d_params = nullptr;
+    double* d_osc = nullptr;
+    double* d_lnl = nullptr;
+    uint32_t* d_flags = nullptr;
+    double* h_params = nullptr;  // pinned
+    double* h_lnl = nullptr;     // pinned
+    uint32_t* h_flags = nullptr; // pinned
+    double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
+    size_t scratch_bytes = 0;
+    size_t osc_smem_limit = 200 * 1024;
+    std::mutex mu;
+    std::string err;
+    float ms_osc = 0.f, ms_rates = 0.f;
+    int launches = 0;
+
+    template <class Tp>
+    Tp* dalloc(size_t n) {
+        void* p = nullptr;
+        CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(Tp)));
+        dev_allocs.push_back(p);
+        return static_cast<Tp*>(p);
+    }
+    template <class Tp>
+    Tp* upload(const Tp* src, size_t n) {
+        Tp* d = dalloc<Tp>(n);
+        if (n) CK(cudaMemcpy(d, src, n * sizeof(Tp), cudaMemcpyHostToDevice));
+        return d;
+    }
+    double* upload_vec(const std::vector<double>& v) { return upload(v.data(), v.size()); }
+    void ensure_scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return;
+        if (d_scratch) CK(cudaFree(d_scratch));
+        d_scratch = nullptr;
+        scratch_bytes = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_scratch), bytes));
+        scratch_bytes = bytes;
+    }
+};
+
+namespace {
+
+// [a][b] table given in either layout -> row-major copy (b fastest)
+std::vector<double> to_row_major(const double* src, int na, int nb, bool col_major) {
+    std::vector<double> out((size_t)na * nb);
+    for (int a = 0; a < na; ++a)
+        for (int b = 0; b < nb; ++b) out[(size_t)a * nb + b] = col_major ? src[(size_t)b * na + a] : src[(size_t)a * nb + b];
+    return out;
+}
+
+void upload_data(solarosc_handle* h, int d, const double* es_day, const double* es_night, const double* cc_day,
+                 const double* cc_night) {
+    const int nZ = h->T.n_cosz;
+    const bool cm = h->cfg.col_major != 0;
+    auto pack = [&](const double* day, const double* night, int nR, double* d_obs, double* d_log) {
+        std::vector<double> obs((size_t)(1 + nZ) * nR), lg(obs.size());
+        std::copy(day, day + nR, obs.begin());
+        std::vector<double> nt = to_row_major(night, nZ, nR, cm);
+        std::copy(nt.begin(), nt.end(), obs.begin() + nR);
+        for (size_t i = 0; i < obs.size(); ++i) lg[i] = obs[i] > 0.0 ? std::log(obs[i]) : 0.0;
+        CK(cudaMemcpy(d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_log, lg.data(), lg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    };
+    pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d]);
+    pack(cc_day, cc_night, h->n_cc[d], h->d_obs_cc[d], h->d_log_cc[d]);
+    h->has_data[d] = true;
+}
+
+void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* c) {
+    REQUIRE(t && c, "tables and config must not be NULL");
+    REQUIRE(c->abi_version == SOLAROSC_ABI_VERSION, "config.abi_version does not match this library");
+    REQUIRE(t->n_etrue > 0 && t->n_cosz > 0 && t->n_cosz_sub > 0, "empty binning");
+    REQUIRE(t->n_layers > 0 && t->n_layers <= SOLAROSC_MAX_LAYERS, "n_layers out of range");
+    REQUIRE(t->n_det > 0 && t->n_det <= kMaxDet, "n_det out of range");
+    REQUIRE(t->e_calc && t->seg_start && t->seg_layer && t->seg_length && t->earth_lookup && t->exposure_weights && t->det,
+            "NULL table pointer");
+    REQUIRE(c->fast || (t->n_solar > 0 && t->solar_ne && t->solar_prod_8b && t->solar_prod_hep),
+            "fast == 0 needs the solar production-region tables");
+    h->cfg = *c;
+    h->device = c->device;
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    if (c->device < 0 || c->device >= n_dev) throw CudaFail{"no such CUDA device"};
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) throw CudaFail{"libsolarosc_b200 holds sm_100a code only; this device is not compute capability 10.x"};
+    h->sm_count = prop.multiProcessorCount;
+    h->osc_smem_limit = std::min<size_t>(200 * 1024, prop.sharedMemPerBlockOptin);
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CK(cudaEventCreate(&e));
+
+    DevTables& T = h->T;
+    T.n_etrue = t->n_etrue; T.n_e = 2 * t->n_etrue; T.n_cosz = t->n_cosz; T.n_sub = t->n_cosz_sub;
+    T.n_paths = t->n_cosz * t->n_cosz_sub; T.n_layers = t->n_layers; T.n_solar = c->fast ? 0 : t->n_solar;
+    T.n_det = t->n_det; T.fast = c->fast != 0; T.earth_unc = c->earth_uncertainty != 0;
+    const int n_seg = t->seg_start[T.n_paths];
+    REQUIRE(t->seg_start[0] == 0 && n_seg > 0, "seg_start must start at 0");
+    T.n_seg = n_seg;
+    T.e_calc = h->upload(t->e_calc, T.n_e);
+    T.path_start = h->upload(t->seg_start, T.n_paths + 1);
+    // Applied order of the steps of each path (reference osc.jl:436-446 and :455-456): step m uses
+    // layer index[n-1-m] paired with length[m] of the stored detector->surface segment list.
+    std::vector<int> app_layer(n_seg);
+    std::vector<double> app_len(n_seg);
+    std::vector<int> row_cost(T.n_cosz, 0);
+    for (int pth = 0; pth < T.n_paths; ++pth) {
+        const int s0 = t->seg_start[pth], n = t->seg_start[pth + 1] - s0;
+        REQUIRE(n > 0, "a path has no segments");
+        for (int m = 0; m < n; ++m) {
+            const int lay = t->seg_layer[s0 + n - 1 - m];
+            REQUIRE(lay >= 1 && lay <= t->n_layers, "segment layer id out of range");
+            app_layer[s0 + m] = lay - 1;
+            app_len[s0 + m] = t->seg_length[s0 + m];
+        }
+        row_cost[pth / T.n_sub] += n;
+    }
+    T.app_layer = h->upload(app_layer.data(), n_seg);
+    T.app_len = h->upload(app_len.data(), n_seg);
+    std::vector<int> order(T.n_cosz);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_cost[a] > row_cost[b]; });
+    T.row_order = h->upload(order.data(), T.n_cosz);
+    T.earth_lookup = h->upload(t->earth_lookup, T.n_layers);
+    T.wz = h->upload(t->exposure_weights, T.n_cosz);
+    T.avg_ne[0] = t->avg_ne_8b; T.avg_ne[1] = t->avg_ne_hep;
+    if (!c->fast) {
+        T.solar_ne = h->upload(t->solar_ne, t->n_solar);
+        T.solar_w[0] = h->upload(t->solar_prod_8b, t->n_solar);
+        T.solar_w[1] = h->upload(t->solar_prod_hep, t->n_solar);
+        T.solar_wsum[0] = std::accumulate(t->solar_prod_8b, t->solar_prod_8b + t->n_solar, 0.0);
+        T.solar_wsum[1] = std::accumulate(t->solar_prod_hep, t->solar_prod_hep + t->n_solar, 0.0);
+    }
+    int off = SOLAROSC_N_FIXED_PARAMS + (T.earth_unc ? T.n_layers : 0);
+    const bool cm = c->col_major != 0;
+    for (int d = 0; d < t->n_det; ++d) {
+        const solarosc_detector& s = t->det[d];
+        DevDetector& D = T.det[d];
+        REQUIRE(s.n_ereco_es > 0 && s.n_ereco_cc > 0, "detector without reco bins");
+        REQUIRE(s.n_bg_es >= 0 && s.n_bg_es <= SOLAROSC_MAX_BG && s.n_bg_cc >= 0 && s.n_bg_cc <= SOLAROSC_MAX_BG,
+                "too many background components");
+        REQUIRE(s.index_es >= 1 && s.index_es <= s.n_ereco_es && s.index_cc >= 1 && s.index_cc <= s.n_ereco_cc,
+                "threshold index out of range");
+        REQUIRE(s.unosc_es_nue_8b && s.unosc_es_nuother_8b && s.unosc_cc_8b && s.unosc_es_nue_hep &&
+                    s.unosc_es_nuother_hep && s.unosc_cc_hep && s.log_e_norm && s.resp_es_nue && s.resp_es_nuother &&
+                    s.resp_cc && s.eff_es_nue && s.eff_es_nuother && s.eff_cc,
+                "NULL detector table pointer");
+        REQUIRE((s.n_bg_es == 0 || (s.raw_bg_es && s.bg_es_sides && s.bg_es_par)) && (s.n_bg_cc == 0 || (s.raw_bg_cc && s.bg_cc_par)),
+                "NULL background table pointer");
+        D.es_mode = s.es_mode != 0; D.cc_mode = s.cc_mode != 0;
+        D.n_es = s.n_ereco_es; D.n_cc = s.n_ereco_cc; D.index_es = s.index_es; D.index_cc = s.index_cc;
+        D.n_bg_es = s.n_bg_es; D.n_bg_cc = s.n_bg_cc;
+        h->n_es[d] = D.n_es; h->n_cc[d] = D.n_cc;
+        h->max_ereco = std::max({h->max_ereco, D.n_es, D.n_cc});
+        const int nT = T.n_etrue;
+        D.u_es_nue_8b = h->upload(s.unosc_es_nue_8b, nT); D.u_es_nuo_8b = h->upload(s.unosc_es_nuother_8b, nT);
+        D.u_cc_8b = h->upload(s.unosc_cc_8b, nT); D.u_es_nue_hep = h->upload(s.unosc_es_nue_hep, nT);
+        D.u_es_nuo_hep = h->upload(s.unosc_es_nuother_hep, nT); D.u_cc_hep = h->upload(s.unosc_cc_hep, nT);
+        D.log_e_norm = h->upload(s.log_e_norm, nT);
+        D.r_es_nue = h->upload_vec(to_row_major(s.resp_es_nue, nT, D.n_es, cm));
+        D.r_es_nuo = h->upload_vec(to_row_major(s.resp_es_nuother, nT, D.n_es, cm));
+        D.r_cc = h->upload_vec(to_row_major(s.resp_cc, nT, D.n_cc, cm));
+        D.eff_es_nue = h->upload(s.eff_es_nue, D.n_es); D.eff_es_nuo = h->upload(s.eff_es_nuother, D.n_es);
+        D.eff_cc = h->upload(s.eff_cc, D.n_cc);
+        D.raw_bg_es = h->upload(s.raw_bg_es, (size_t)D.n_bg_es * D.n_es);
+        D.raw_bg_cc = h->upload(s.raw_bg_cc, (size_t)D.n_bg_cc * D.n_cc);
+        D.n_norm_es = 0; D.n_norm_cc = 0;
+        for (int i = 0; i < D.n_bg_es; ++i) {
+            if (s.bg_es_par[i] != 0) {  // face areas of propagation_bg.jl:6-18
+                const int side = s.bg_es_sides[i];
+                D.bg_es_area[i] = side == 0 ? 2 * 12e2 * 64e2 : (side == 1 ? 2 * 12e2 * 12e2 : 2 * 12e2 * 64e2 + 2 * 12e2 * 12e2);
+                ++D.n_norm_es;
+            } else
+                D.bg_es_area[i] = 0.0;
+        }
+        for (int i = 0; i < D.n_bg_cc; ++i) D.bg_cc_norm[i] = s.bg_cc_par[i] != 0 ? D.n_norm_cc++ : -1;
+        D.param_off = off;
+        off += D.n_norm_es + D.n_norm_cc;
+        const size_t ne = (size_t)(1 + T.n_cosz) * D.n_es, nc = (size_t)(1 + T.n_cosz) * D.n_cc;
+        h->d_obs_es[d] = h->dalloc<double>(ne); h->d_log_es[d] = h->dalloc<double>(ne);
+        h->d_obs_cc[d] = h->dalloc<double>(nc); h->d_log_cc[d] = h->dalloc<double>(nc);
+        CK(cudaMemset(h->d_obs_es[d], 0, ne * sizeof(double))); CK(cudaMemset(h->d_log_es[d], 0, ne * sizeof(double)));
+        CK(cudaMemset(h->d_obs_cc[d], 0, nc * sizeof(double))); CK(cudaMemset(h->d_log_cc[d], 0, nc * sizeof(double)));
+        D.obs_es = h->d_obs_es[d]; D.logobs_es = h->d_log_es[d]; D.obs_cc = h->d_obs_cc[d]; D.logobs_cc = h->d_log_cc[d];
+        if (s.obs_es_day && s.obs_es_night && s.obs_cc_day && s.obs_cc_night)
+            upload_data(h, d, s.obs_es_day, s.obs_es_night, s.obs_cc_day, s.obs_cc_night);
+    }
+    h->P = off;
+    T.n_params = off;
+    h->chunk = c->max_batch > 0 ? c->max_batch : 4096;
+    const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
+    h->d_params = h->dalloc<double>((size_t)h->chunk * h->P);
+    h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
+    h->d_lnl = h->dalloc<double>(h->chunk);
+    h->d_flags = h->dalloc<uint32_t>(h->chunk);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_params), (size_t)h->chunk * h->P * sizeof(double)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_lnl), (size_t)h->chunk * sizeof(double)));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), (size_t)h->chunk * sizeof(uint32_t)));
+    const size_t rs = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    if (rs > prop.sharedMemPerBlockOptin) throw ArgFail{"binning too large for the rate kernel's shared-memory tile"};
+    CK(cudaFuncSetAttribute(rates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
+}
+
+// ---- launches ------------------------------------------------------------------------------------
+void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point_step, double* d_p1e, cudaStream_t st) {
+    const DevTables& T = h->T;
+    // coarse bins per CTA: the whole spectrum when the batch alone fills the GPU, otherwise split the
+    // energy axis so that about two CTAs per SM exist; never more than shared memory holds
+    const size_t per_cb = osc_smem_bytes(T.n_layers, 1);
+    const int cb_max = (int)std::max<size_t>(1, h->osc_smem_limit / per_cb);
+    int want_chunks = (2 * h->sm_count + n_osc - 1) / n_osc;
+    want_chunks = std::max(1, std::min(want_chunks, std::max(1, T.n_etrue / 4)));
+    int cb = (T.n_etrue + want_chunks - 1) / want_chunks;
+    cb = std::max(1, std::min(cb, cb_max));
+    const int n_chunks = (T.n_etrue + cb - 1) / cb;
+    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step};
+    osc_kernel<<<n_osc * n_chunks, kOscThreads, osc_smem_bytes(T.n_layers, cb), st>>>(T, L, d_params, h->d_osc, d_p1e);
+    CK(cudaGetLastError());
+    ++h->launches;
+}
+
+void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, int mode, int det_only, RatesOut O,
+                  cudaStream_t st) {
+    const DevTables& T = h->T;
+    RatesLaunch L{};
+    L.n_points = n; L.group = group; L.param_stride = h->P; L.mode = mode; L.det_only = det_only;
+    const int d = det_only >= 0 ? det_only : 0;
+    const bool cm = h->cfg.col_major != 0;
+    L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? T.n_cosz : 1;
+    L.s_row_cc = cm ? 1 : h->n_cc[d]; L.s_j_cc = cm ? T.n_cosz : 1;
+    rates_kernel<<<n, kRatesThreads, rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco), st>>>(T, L, d_params, h->d_osc, O);
+    CK(cudaGetLastError());
+    ++h->launches;
+}
+
+void check_data(solarosc_handle* h, int det_only) {
+    for (int d = 0; d < h->T.n_det; ++d)
+        if ((det_only < 0 || d == det_only) && !h->has_data[d])
+            throw ArgFail{"observed data not set for a detector (pass obs_* at create or call solarosc_set_data)"};
+}
+
+template <class F>
+int guarded(solarosc_handle* h, F&& body) {
+    if (!h) return SOLAROSC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    try {
+        CK(cudaSetDevice(h->device));
+        return body();
+    } catch (const ArgFail& e) {
+        h->err = e.msg;
+        return SOLAROSC_ERR_ARG;
+    } catch (const CudaFail& e) {
+        h->err = e.msg;
+        return SOLAROSC_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        h->err = "host allocation failed";
+        return SOLAROSC_ERR_ALLOC;
+    } catch (...) {
+        h->err = "unexpected exception";
+        return SOLAROSC_ERR_ARG;
+    }
+}
+
+// Host-buffer likelihood evaluation, chunked.
+int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t group, double* out, uint32_t* flags) {
+    REQUIRE(params && out, "params and out_lnl must not be NULL");
+    REQUIRE(group >= 1 && n % group == 0, "n_points must be a multiple of group");
+    REQUIRE(group <= (size_t)h->chunk, "group larger than max_batch");
+    check_data(h, -1);
+    h->ms_osc = h->ms_rates = 0.f;
+    h->launches = 0;
+    const size_t step = ((size_t)h->chunk / group) * group;
+    bool neg = false;
+    for (size_t b0 = 0; b0 < n; b0 += step) {
+        const int nb = (int)std::min(step, n - b0);
+        std::memcpy(h->h_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double));
+        CK(cudaMemcpyAsync(h->d_params, h->h_params, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        launch_osc(h, h->d_params, nb / (int)group, (int)group, nullptr, h->stream);
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        RatesOut O{};
+        O.lnl = h->d_lnl; O.flags = h->d_flags;
+        launch_rates(h, h->d_params, nb, (int)group, kModeLlh, -1, O, h->stream);
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaMemcpyAsync(h->h_lnl, h->d_lnl, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_flags, h->d_flags, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float a = 0.f, c = 0.f;
+        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+        CK(cudaEventElapsedTime(&c, h->ev[1], h->ev[2]));
+        h->ms_osc += a; h->ms_rates += c;
+        std::memcpy(out + b0, h->h_lnl, nb * sizeof(double));
+        if (flags) std::memcpy(flags + b0, h->h_flags, nb * sizeof(uint32_t));
+        for (int i = 0; i < nb; ++i) neg |= (h->h_flags[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+    }
+    if (neg) {
+        h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
+        return SOLAROSC_ERR_NEGATIVE_RATE;
+    }
+    return SOLAROSC_OK;
+}
+
+// Rates / per-bin evaluation of one detector; outputs copied chunk by chunk into the host arrays.
+int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params, size_t n, double* es_day, double* es_night,
+                     double* cc_day, double* cc_night, double* bg_es, double* bg_cc) {
+    REQUIRE(params, "params must not be NULL");
+    REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
+    if (mode == kModePerbin) check_data(h, det);
+    const int nZ = h->T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
+    const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
+    const int step = std::max(1, std::min(h->chunk, 1024));
+    h->ensure_scratch(per * step * sizeof(double));
+    h->launches = 0;
+    for (size_t b0 = 0; b0 < n; b0 += step) {
+        const int nb = (int)std::min<size_t>(step, n - b0);
+        std::memcpy(h->h_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double));
+        CK(cudaMemcpyAsync(h->d_params, h->h_params, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
+        double* s = h->d_scratch;
+        RatesOut O{};
+        O.es_day = s; s += (size_t)nb * nE;
+        O.es_night = s; s += (size_t)nb * nZ * nE;
+        O.cc_day = s; s += (size_t)nb * nC;
+        O.cc_night = s; s += (size_t)nb * nZ * nC;
+        O.bg_es = s; s += (size_t)nb * nE;
+        O.bg_cc = s;
+        launch_rates(h, h->d_params, nb, 1, mode, det, O, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+        auto back = [&](double* dst, const double* src, size_t per_pt) {
+            if (dst) CK(cudaMemcpy(dst + b0 * per_pt, src, (size_t)nb * per_pt * sizeof(double), cudaMemcpyDeviceToHost));
+        };
+        back(es_day, O.es_day, nE); back(es_night, O.es_night, (size_t)nZ * nE);
+        back(cc_day, O.cc_day, nC); back(cc_night, O.cc_night, (size_t)nZ * nC);
+        if (mode == kModeRates) { back(bg_es, O.bg_es, nE); back(bg_cc, O.bg_cc, nC); }
+    }
+    return SOLAROSC_OK;
+}
+
+// host transpose of per-point [a][b] blocks into [b][a] (Julia layout) in place via a temporary
+void transpose_blocks(double* x, size_t n, int na, int nb) {
+    std::vector<double> tmp((size_t)na * nb);
+    for (size_t p = 0; p < n; ++p) {
+        double* blk = x + p * na * nb;
+        for (int a = 0; a < na; ++a)
+            for (int b = 0; b < nb; ++b) tmp[(size_t)b * na + a] = blk[(size_t)a * nb + b];
+        std::copy(tmp.begin(), tmp.end(), blk);
+    }
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int solarosc_abi_version(void) { return SOLAROSC_ABI_VERSION; }
+
+solarosc_handle* solarosc_create(const solarosc_tables* tables, const solarosc_config* config, int* status) {
+    solarosc_handle* h = nullptr;
+    int st = SOLAROSC_OK;
+    try {
+        h = new solarosc_handle();
+        build(h, tables, config);
+    } catch (const ArgFail& e) {
+        g_create_error = e.msg; st = SOLAROSC_ERR_ARG;
+    } catch (const CudaFail& e) {
+        g_create_error = e.msg; st = SOLAROSC_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        g_create_error = "host allocation failed"; st = SOLAROSC_ERR_ALLOC;
+    } catch (...) {
+        g_create_error = "unexpected exception"; st = SOLAROSC_ERR_ARG;
+    }
+    if (st != SOLAROSC_OK && h) {
+        solarosc_destroy(h);
+        h = nullptr;
+    }
+    if (status) *status = st;
+    return h;
+}
+
+void solarosc_destroy(solarosc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->h_params) cudaFreeHost(h->h_params);
+    if (h->h_lnl) cudaFreeHost(h->h_lnl);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* solarosc_last_error(const solarosc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int solarosc_n_params(const solarosc_handle* h) { return h ? h->P : -1; }
+
+int solarosc_set_data(solarosc_handle* h, int det, const double* es_day, const double* es_night, const double* cc_day,
+                      const double* cc_night) {
+    return guarded(h, [&]() {
+        REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
+        REQUIRE(es_day && es_night && cc_day && cc_night, "data pointers must not be NULL");
+        CK(cudaStreamSynchronize(h->stream));
+        upload_data(h, det, es_day, es_night, cc_day, cc_night);
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_eval_llh(solarosc_handle* h, const double* params, size_t n, double* out, uint32_t* flags) {
+    return guarded(h, [&]() { return n == 0 ? (int)SOLAROSC_OK : eval_llh_host(h, params, n, 1, out, flags); });
+}
+
+int solarosc_eval_llh_grouped(solarosc_handle* h, const double* params, size_t n, size_t group, double* out,
+                              uint32_t* flags) {
+    return guarded(h, [&]() { return n == 0 ? (int)SOLAROSC_OK : eval_llh_host(h, params, n, group, out, flags); });
+}
+
+int solarosc_eval_rates(solarosc_handle* h, int det, const double* params, size_t n, double* es_day, double* es_night,
+                        double* cc_day, double* cc_night, double* bg_es, double* bg_cc) {
+    return guarded(h, [&]() {
+        return n == 0 ? (int)SOLAROSC_OK
+                      : eval_arrays_host(h, det, kModeRates, params, n, es_day, es_night, cc_day, cc_night, bg_es, bg_cc);
+    });
+}
+
+int solarosc_eval_perbin(solarosc_handle* h, int det, const double* params, size_t n, double* es_day, double* es_night,
+                         double* cc_day, double* cc_night) {
+    return guarded(h, [&]() {
+        return n == 0 ? (int)SOLAROSC_OK
+                      : eval_arrays_host(h, det, kModePerbin, params, n, es_day, es_night, cc_day, cc_night, nullptr, nullptr);
+    });
+}
+
+int solarosc_eval_oscprobs(solarosc_handle* h, const double* params, size_t n, double* day_8b, double* night_8b,
+                           double* day_hep, double* night_hep) {
+    return guarded(h, [&]() {
+        if (n == 0) return (int)SOLAROSC_OK;
+        REQUIRE(params, "params must not be NULL");
+        const int nT = h->T.n_etrue, nZ = h->T.n_cosz, nrow = 1 + nZ;
+        std::vector<double> host((size_t)h->chunk * 2 * nrow * nT);
+        h->launches = 0;
+        for (size_t b0 = 0; b0 < n; b0 += h->chunk) {
+            const int nb = (int)std::min<size_t>(h->chunk, n - b0);
+            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
+            CK(cudaMemcpyAsync(host.data(), h->d_osc, (size_t)nb * 2 * nrow * nT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < nb; ++i) {
+                const double* s8 = host.data() + (size_t)i * 2 * nrow * nT;
+                const double* sh = s8 + (size_t)nrow * nT;
+                const size_t b = b0 + i;
+                if (day_8b) std::copy(s8, s8 + nT, day_8b + b * nT);
+                if (day_hep) std::copy(sh, sh + nT, day_hep + b * nT);
+                if (night_8b) std::copy(s8 + nT, s8 + (size_t)nrow * nT, night_8b + b * nZ * nT);
+                if (night_hep) std::copy(sh + nT, sh + (size_t)nrow * nT, night_hep + b * nZ * nT);
+            }
+        }
+        if (h->cfg.col_major) {
+            if (night_8b) transpose_blocks(night_8b, n, nZ, nT);
+            if (night_hep) transpose_blocks(night_hep, n, nZ, nT);
+        }
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_eval_p1e(solarosc_handle* h, const double* params, size_t n, double* p1e) {
+    return guarded(h, [&]() {
+        if (n == 0) return (int)SOLAROSC_OK;
+        REQUIRE(params && p1e, "params and p1e must not be NULL");
+        const size_t per = (size_t)h->T.n_paths * h->T.n_e;
+        const int step = std::max(1, std::min(h->chunk, 256));
+        h->ensure_scratch(per * step * sizeof(double));
+        h->launches = 0;
+        for (size_t b0 = 0; b0 < n; b0 += step) {
+            const int nb = (int)std::min<size_t>(step, n - b0);
+            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launch_osc(h, h->d_params, nb, 1, h->d_scratch, h->stream);
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaMemcpy(p1e + b0 * per, h->d_scratch, (size_t)nb * per * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        if (h->cfg.col_major) transpose_blocks(p1e, n, h->T.n_paths, h->T.n_e);
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_eval_llh_device(solarosc_handle* h, const double* d_params, size_t n, size_t group, double* d_lnl,
+                             uint32_t* d_flags, void* stream) {
+    return guarded(h, [&]() {
+        if (n == 0) return (int)SOLAROSC_OK;
+        REQUIRE(d_params && d_lnl, "device pointers must not be NULL");
+        if (group == 0) group = 1;
+        REQUIRE(n % group == 0 && group <= (size_t)h->chunk, "n_points must be a multiple of group (<= max_batch)");
+        check_data(h, -1);
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+        const size_t step = ((size_t)h->chunk / group) * group;
+        h->launches = 0;
+        for (size_t b0 = 0; b0 < n; b0 += step) {
+            const int nb = (int)std::min(step, n - b0);
+            launch_osc(h, d_params + b0 * h->P, nb / (int)group, (int)group, nullptr, st);
+            RatesOut O{};
+            O.lnl = d_lnl + b0;
+            O.flags = d_flags ? d_flags + b0 : nullptr;
+            launch_rates(h, d_params + b0 * h->P, nb, (int)group, kModeLlh, -1, O, st);
+        }
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_poisson_llh(solarosc_handle* h, const double* expected, const double* measured, size_t n_vec, size_t len,
+                         double* out, uint32_t* out_flags) {
+    return guarded(h, [&]() {
+        if (n_vec == 0) return (int)SOLAROSC_OK;
+        REQUIRE(expected && measured && out, "NULL pointer");
+        const size_t tot = n_vec * len;
+        h->ensure_scratch((2 * tot + n_vec) * sizeof(double) + n_vec * sizeof(uint32_t));
+        double* de = h->d_scratch;
+        double* dm = de + tot;
+        double* dout = dm + tot;
+        uint32_t* df = reinterpret_cast<uint32_t*>(dout + n_vec);
+        CK(cudaMemcpyAsync(de, expected, tot * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dm, measured, tot * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        poisson_kernel<<<(unsigned)n_vec, 256, 0, h->stream>>>(de, dm, len, dout, df);
+        CK(cudaGetLastError());
+        h->launches = 1;
+        CK(cudaMemcpyAsync(out, dout, n_vec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<uint32_t> fl(n_vec);
+        CK(cudaMemcpyAsync(fl.data(), df, n_vec * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        bool neg = false;
+        for (size_t i = 0; i < n_vec; ++i) {
+            if (out_flags) out_flags[i] = fl[i];
+            neg |= (fl[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+        }
+        return neg ? (int)SOLAROSC_ERR_NEGATIVE_RATE : (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_last_timing(const solarosc_handle* h, float* ms_osc, float* ms_rates) {
+    if (!h) return -1;
+    if (ms_osc) *ms_osc = h->ms_osc;
+    if (ms_rates) *ms_rates = h->ms_rates;
+    return h->launches;
+}
+
+}  // extern "C"

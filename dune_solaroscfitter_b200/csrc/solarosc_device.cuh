@@ -1,0 +1,218 @@
+// solarosc_device.cuh -- device-side tables and FP64 math helpers for libsolarosc_b200.
+//
+// Everything here is written for sm_100a (B200).  The hot path is FP64-pipe bound (SURVEY.md
+// section 8(d)): no tensor-core shaped work exists in it, so the design rules that matter are
+// warp-uniform control flow, conflict-free shared-memory tables and as few FP64 instructions per
+// Earth-layer step as the algebra allows.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/solarosc_b200.h"
+
+namespace solarosc {
+
+constexpr double kGF = 5.4489e-5;                 // reference osc.jl:51
+constexpr double kPhase = 2.5338653580781976;     // reference osc.jl:361
+constexpr double kDm31 = 2.5e-3;                  // reference osc.jl:44 (theta23, deltaCP drop out of P1e)
+constexpr int kMaxDet = 4;
+
+struct DevDetector {
+    int es_mode, cc_mode, n_es, n_cc, index_es, index_cc, n_bg_es, n_bg_cc, n_norm_es, n_norm_cc, param_off;
+    // all [n_etrue]
+    const double *u_es_nue_8b, *u_es_nuo_8b, *u_cc_8b, *u_es_nue_hep, *u_es_nuo_hep, *u_cc_hep, *log_e_norm;
+    // responses stored [n_etrue][n_ereco] (j fastest), efficiencies [n_ereco]
+    const double *r_es_nue, *r_es_nuo, *r_cc, *eff_es_nue, *eff_es_nuo, *eff_cc;
+    const double *raw_bg_es, *raw_bg_cc;  // [n_bg][n_ereco]
+    double bg_es_area[SOLAROSC_MAX_BG];   // face area per ES component (0 => not scaled by a nuisance)
+    int bg_cc_norm[SOLAROSC_MAX_BG];      // index of the CC nuisance scaling component i, -1 => fixed
+    // data stored [1+n_cosz][n_ereco] (row 0 = day) and log(data) alongside
+    const double *obs_es, *obs_cc, *logobs_es, *logobs_cc;
+};
+
+struct DevTables {
+    int n_etrue, n_e, n_cosz, n_sub, n_paths, n_layers, n_solar, n_seg, n_det, n_params;
+    int fast, earth_unc;
+    const double* e_calc;      // [n_e]
+    const int* path_start;     // [n_paths+1]
+    const int* app_layer;      // [n_seg] 0-based layer of the m-th APPLIED step of each path
+    const double* app_len;     // [n_seg] its length [km]
+    const int* row_order;      // [n_cosz] coarse zenith rows, longest paths first
+    const double* earth_lookup;// [n_layers]
+    const double* wz;          // [n_cosz]
+    double avg_ne[2];
+    const double* solar_ne;    // [n_solar]
+    const double* solar_w[2];  // production fractions 8B / hep
+    double solar_wsum[2];
+    DevDetector det[kMaxDet];
+};
+
+// ------------------------------------------------------------------------------------------
+// sin/cos of a phase that is known to be moderate (|x| < 2^30): two-constant Cody-Waite
+// reduction done with FMAs (x - k*pi/2 is exact in the first FMA because k*PIO2_HI needs at most
+// 53+31 bits and the difference is < 1 in magnitude on the grid of ulp(PIO2_HI)), then the
+// classic fdlibm minimax kernels on [-pi/4, pi/4].  About 22 FP64 instructions against ~40 for
+// CUDA's sincos(), which also carries a Payne-Hanek slow path these phases can never take.
+// The largest phase of the default configuration is c*L*dm31/E ~ 7e4 rad.
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define SOLAROSC_HD __host__ __device__ __forceinline__
+__device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+__device__ __forceinline__ int lo_int(double x) { return __double2loint(x); }
+#else
+// The same helpers compile for the host so that tests can run the exact kernel arithmetic on the
+// CPU (tests/csrc/host_math_check.cu); the library itself never executes them there.
+#define SOLAROSC_HD __host__ __device__ inline
+inline double rsq(double x) { return 1.0 / std::sqrt(x); }
+inline int lo_int(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
+#endif
+
+SOLAROSC_HD void sincos_phase(double x, double& s, double& c) {
+    const double kTwoOverPi = 6.36619772367581382433e-01;
+    const double kPio2Hi = 1.57079632679489655800e+00;
+    const double kPio2Lo = 6.12323399573676603587e-17;
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: forces round-to-nearest-integer
+    double kd = fma(x, kTwoOverPi, kMagic);
+    int q = lo_int(kd);
+    kd -= kMagic;
+    double r = fma(-kd, kPio2Hi, x);
+    r = fma(-kd, kPio2Lo, r);
+    double z = r * r;
+    // sin kernel
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double sr = fma(z * r, ps, r);
+    // cos kernel
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant: q mod 4 = 0: (s,c)=(sr,cr) 1: (cr,-sr) 2: (-sr,-cr) 3: (-cr,sr)
+    double ss = (q & 1) ? cr : sr;
+    double cc = (q & 1) ? sr : cr;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Eigen-system of the matter Hamiltonian in the vacuum mass basis.
+//
+// The reference diagonalises H = U diag(0,dm21,dm31) U^dagger + rho*E * diag(0,-1,-1)
+// (osc.jl:370-388, complex Hermitian 3x3).  U = U23 * D(delta) * O * D(delta)^dagger with
+// O = U13(real) * U12 real orthogonal, and both U23 and D act trivially on the electron row, so
+// H is unitarily equivalent, by a matter-independent rotation, to the REAL symmetric
+//     S = diag(0, dm21, dm31) + a * u u^T  - a*I,     a = rho*E,  u = (c12 c13, s12 c13, s13),
+// and P1e = |<nu_1| prod_k exp(-i S_k t_k) |u>|^2 does not depend on theta23 or deltaCP at all.
+// S is a rank-one update of a diagonal matrix: eigenvalues from the trigonometric solution of the
+// characteristic cubic, eigenvectors from v_i[j] ~ u_j * prod_{k != j} (mu_i - m_k) (no
+// divisions, well defined when a or some u_j vanish).  Only eigenvalue differences are
+// returned (the common phase drops out of |amplitude|^2).
+// q[3*j+i] = component j of eigenvector i.
+// ------------------------------------------------------------------------------------------
+SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, double u2, double u3,
+                                             double q[9], double& w2, double& w3) {
+    const double m[3] = {0.0, d21, d31};
+    const double u[3] = {u1, u2, u3};
+    double s11 = a * u1 * u1, s22 = fma(a * u2, u2, d21), s33 = fma(a * u3, u3, d31);
+    double s12 = a * u1 * u2, s13 = a * u1 * u3, s23 = a * u2 * u3;
+    double mu[3];
+    double p1 = s12 * s12 + s13 * s13 + s23 * s23;
+    if (p1 == 0.0) {
+        mu[0] = s11; mu[1] = s22; mu[2] = s33;
+    } else {
+        double tq = (s11 + s22 + s33) * (1.0 / 3.0);
+        double b11 = s11 - tq, b22 = s22 - tq, b33 = s33 - tq;
+        double p2 = b11 * b11 + b22 * b22 + b33 * b33 + 2.0 * p1;
+        double p = sqrt(p2 * (1.0 / 6.0));
+        double ip = 1.0 / p;
+        b11 *= ip; b22 *= ip; b33 *= ip;
+        double c12 = s12 * ip, c13 = s13 * ip, c23 = s23 * ip;
+        double det = b11 * (b22 * b33 - c23 * c23) - c12 * (c12 * b33 - c23 * c13) + c13 * (c12 * c23 - b22 * c13);
+        double r = fmin(1.0, fmax(-1.0, 0.5 * det));
+        double phi = acos(r) * (1.0 / 3.0);
+        double sp, cp;
+        sincos_phase(phi, sp, cp);
+        // cos(phi + 2pi/3) = -cp/2 - sqrt(3)/2 * sp
+        mu[2] = fma(2.0 * p, cp, tq);
+        mu[0] = fma(2.0 * p, fma(-0.8660254037844386, sp, -0.5 * cp), tq);
+        mu[1] = 3.0 * tq - mu[0] - mu[2];
+    }
+    // ascending order (only needed on the diagonal shortcut, cheap)
+    if (mu[0] > mu[1]) { double t = mu[0]; mu[0] = mu[1]; mu[1] = t; }
+    if (mu[1] > mu[2]) { double t = mu[1]; mu[1] = mu[2]; mu[2] = t; }
+    if (mu[0] > mu[1]) { double t = mu[0]; mu[0] = mu[1]; mu[1] = t; }
+    // Root i sits next to pole m_i (interlacing).  Its shift delta_i = mu_i - m_i is re-derived from
+    // the secular equation 1 + a sum_k u_k^2/(m_k - mu) = 0, solved for the i-th term:
+    //     delta_i = a u_i^2 g_k g_l / (g_k g_l + a (u_k^2 g_l + u_l^2 g_k)),   g_x = m_x - mu_i,
+    // an identity that only uses the well-conditioned gaps to the OTHER poles, so delta_i keeps
+    // full relative accuracy when a u_i^2 is far below the rounding noise of the cubic's roots
+    // (weak matter, tiny theta13) and is exactly 0 when state i decouples (u_i = 0).
+    double dl[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int k = (i == 0) ? 1 : 0, l = (i == 2) ? 1 : 2;
+        const double gk = m[k] - mu[i], gl = m[l] - mu[i];
+        const double den = fma(a, fma(u[k] * u[k], gl, u[l] * u[l] * gk), gk * gl);
+        const double num = a * u[i] * u[i] * gk * gl;
+        const double d = (den != 0.0) ? num / den : mu[i] - m[i];
+        dl[i] = d;
+        // eigenvector: v[j] ~ u_j prod_{x != j} (mu_i - m_x)
+        const double vi = u[i] * (gk * gl), vk = -u[k] * (d * gl), vl = -u[l] * (d * gk);
+        const double n2 = vi * vi + vk * vk + vl * vl;
+        double e[3];
+        if (n2 > 0.0 && n2 < 1e300) {
+            const double rn = rsq(n2);
+            e[i] = vi * rn; e[k] = vk * rn; e[l] = vl * rn;
+        } else {  // exactly decoupled state (u_i == 0), or everything underflowed
+            e[i] = 1.0; e[k] = 0.0; e[l] = 0.0;
+        }
+        q[0 + i] = e[0]; q[3 + i] = e[1]; q[6 + i] = e[2];
+    }
+    w2 = (m[1] - m[0]) + (dl[1] - dl[0]);
+    w3 = (m[2] - m[0]) + (dl[2] - dl[0]);
+}
+
+// One constant-density step of the state vector in the vacuum mass basis:
+//   psi <- Q diag(1, e^{-i phi2}, e^{-i phi3}) Q^T psi      (reference osc_kernel, osc.jl:360-364,
+// applied to a vector instead of forming the 3x3 product of osc.jl:442; 44 FMA-pipe operations and
+// two sincos instead of ~400 flops and three complex exponentials).  e points at this (energy,
+// layer) entry of the eigen table, cs is the stride between its 11 components.
+SOLAROSC_HD void earth_step(const double* e, size_t cs, double len, double& ar, double& ai, double& br, double& bi,
+                            double& cr, double& ci) {
+    const double q00 = e[0], q01 = e[cs], q02 = e[2 * cs];
+    const double q10 = e[3 * cs], q11 = e[4 * cs], q12 = e[5 * cs];
+    const double q20 = e[6 * cs], q21 = e[7 * cs], q22 = e[8 * cs];
+    double s2, c2, s3, c3;
+    sincos_phase(len * e[9 * cs], s2, c2);
+    sincos_phase(len * e[10 * cs], s3, c3);
+    const double w0r = fma(q20, cr, fma(q10, br, q00 * ar)), w0i = fma(q20, ci, fma(q10, bi, q00 * ai));
+    const double w1r = fma(q21, cr, fma(q11, br, q01 * ar)), w1i = fma(q21, ci, fma(q11, bi, q01 * ai));
+    const double w2r = fma(q22, cr, fma(q12, br, q02 * ar)), w2i = fma(q22, ci, fma(q12, bi, q02 * ai));
+    const double x1r = fma(w1i, s2, w1r * c2), x1i = fma(-w1r, s2, w1i * c2);
+    const double x2r = fma(w2i, s3, w2r * c3), x2i = fma(-w2r, s3, w2i * c3);
+    ar = fma(q02, x2r, fma(q01, x1r, q00 * w0r)); ai = fma(q02, x2i, fma(q01, x1i, q00 * w0i));
+    br = fma(q12, x2r, fma(q11, x1r, q10 * w0r)); bi = fma(q12, x2i, fma(q11, x1i, q10 * w0i));
+    cr = fma(q22, x2r, fma(q21, x1r, q20 * w0r)); ci = fma(q22, x2i, fma(q21, x1i, q20 * w0i));
+}
+
+// MSW survival probability pieces (reference osc.jl:77-90): returns cos(2 theta12_matter)
+SOLAROSC_HD double msw_c2m(double e, double ne, double dm21, double one_m_s13sq, double c2) {
+    double acc = 2.0 * 1.4142135623730951 * ne * kGF * e * one_m_s13sq;
+    double x = c2 - acc / dm21;
+    return x * rsq(fma(x, x, 1.0 - c2 * c2));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace solarosc

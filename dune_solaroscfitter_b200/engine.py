@@ -1,0 +1,163 @@
+"""``SolarOscEngine``: one handle of the C-ABI library, batched over parameter points.
+
+This is the Python face of ``include/solarosc_b200.h``; all arithmetic happens in the CUDA
+kernels behind ``libsolarosc_b200.so``.  The per-call semantics mirror the reference functions
+named in the header (``total_llh``, ``expected_rates``, ``make_perbin_likelihood``,
+``compute_shared_osc_probs``, ``osc_prob_earth``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, abi
+
+
+class SolarOscError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"solarosc status {status}: {msg}")
+        self.status = status
+
+
+class NegativeRateError(SolarOscError):
+    """Some expected rate was <= -1e-3 (the reference raises: likelihood_statistical.jl:9-14)."""
+
+
+def _dp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class SolarOscEngine:
+    def __init__(self, shared: Mapping, detectors: Optional[Sequence[Mapping]] = None,
+                 data: Optional[Sequence[Optional[Mapping]]] = None, *, device: int = 0, fast: bool = True,
+                 earth_uncertainty: bool = True, col_major: bool = False, max_batch: int = 0,
+                 es_mode: bool = True, cc_mode: bool = True, det_names: Optional[Sequence[str]] = None):
+        self._L = _lib.load()
+        if data is not None and isinstance(data, Mapping):
+            data = [data]
+        self.packed = abi.PackedTables(shared, detectors, data, es_mode=es_mode, cc_mode=cc_mode, col_major=col_major)
+        self.cfg = abi.make_config(device, fast, earth_uncertainty, col_major, max_batch)
+        st = C.c_int(0)
+        self._h = self._L.solarosc_create(C.byref(self.packed.struct), C.byref(self.cfg), C.byref(st))
+        if not self._h:
+            raise SolarOscError(st.value, (self._L.solarosc_last_error(None) or b"").decode())
+        self.n_params = self._L.solarosc_n_params(self._h)
+        self.param_names = self.packed.param_names(earth_uncertainty, det_names)
+        self.col_major = bool(col_major)
+        self.n_etrue, self.n_cosz, self.n_paths = self.packed.n_etrue, self.packed.n_cosz, self.packed.n_paths
+        self.device = device
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.solarosc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def _check(self, status: int):
+        if status == abi.OK:
+            return
+        msg = (self._L.solarosc_last_error(self._h) or b"").decode()
+        if status == abi.ERR_NEGATIVE_RATE:
+            raise NegativeRateError(status, msg)
+        raise SolarOscError(status, msg)
+
+    def _params(self, params) -> np.ndarray:
+        p = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=np.float64)))
+        if p.shape[1] != self.n_params:
+            raise ValueError(f"parameter matrix must have {self.n_params} columns {self.param_names}, got {p.shape[1]}")
+        return p
+
+    def _night(self, n, n_ereco):
+        return np.empty((n, n_ereco, self.n_cosz) if self.col_major else (n, self.n_cosz, n_ereco))
+
+    # -- API --------------------------------------------------------------------------------------
+    def set_data(self, data: Mapping, det: int = 0):
+        a = [np.ascontiguousarray(data[k], dtype=np.float64) for k in ("ES_day", "ES_night", "CC_day", "CC_night")]
+        self._check(self._L.solarosc_set_data(self._h, det, *[_dp(x) for x in a]))
+
+    def eval_llh(self, params, group: int = 1, return_flags: bool = False, raise_on_negative: bool = False):
+        p = self._params(params)
+        out = np.empty(len(p))
+        fl = np.zeros(len(p), dtype=np.uint32)
+        fp = fl.ctypes.data_as(C.POINTER(C.c_uint32))
+        if group == 1:
+            st = self._L.solarosc_eval_llh(self._h, _dp(p), len(p), _dp(out), fp)
+        else:
+            st = self._L.solarosc_eval_llh_grouped(self._h, _dp(p), len(p), group, _dp(out), fp)
+        if st != abi.ERR_NEGATIVE_RATE or raise_on_negative:
+            self._check(st)
+        return (out, fl) if return_flags else out
+
+    def eval_rates(self, params, det: int = 0) -> Dict[str, np.ndarray]:
+        p = self._params(params)
+        n = len(p)
+        nes, ncc = self.packed.n_ereco[det]
+        r = dict(ES_day=np.empty((n, nes)), ES_night=self._night(n, nes), CC_day=np.empty((n, ncc)),
+                 CC_night=self._night(n, ncc), BG_ES_tot=np.empty((n, nes)), BG_CC_tot=np.empty((n, ncc)))
+        self._check(self._L.solarosc_eval_rates(self._h, det, _dp(p), n, _dp(r["ES_day"]), _dp(r["ES_night"]),
+                                                _dp(r["CC_day"]), _dp(r["CC_night"]), _dp(r["BG_ES_tot"]), _dp(r["BG_CC_tot"])))
+        return r
+
+    def eval_perbin(self, params, det: int = 0) -> Dict[str, np.ndarray]:
+        p = self._params(params)
+        n = len(p)
+        nes, ncc = self.packed.n_ereco[det]
+        r = dict(ES_day=np.empty((n, nes)), ES_night=self._night(n, nes), CC_day=np.empty((n, ncc)), CC_night=self._night(n, ncc))
+        self._check(self._L.solarosc_eval_perbin(self._h, det, _dp(p), n, _dp(r["ES_day"]), _dp(r["ES_night"]),
+                                                 _dp(r["CC_day"]), _dp(r["CC_night"])))
+        return r
+
+    def eval_oscprobs(self, params) -> Dict[str, np.ndarray]:
+        p = self._params(params)
+        n, nT = len(p), self.n_etrue
+        r = dict(nue_8B_day=np.empty((n, nT)), nue_8B_night=self._night(n, nT),
+                 nue_hep_day=np.empty((n, nT)), nue_hep_night=self._night(n, nT))
+        self._check(self._L.solarosc_eval_oscprobs(self._h, _dp(p), n, _dp(r["nue_8B_day"]), _dp(r["nue_8B_night"]),
+                                                   _dp(r["nue_hep_day"]), _dp(r["nue_hep_night"])))
+        for k in ("8B_day", "8B_night", "hep_day", "hep_night"):
+            r["nuother_" + k] = 1 - r["nue_" + k]   # unitarity, propagation_osc.jl:140-144
+        return r
+
+    def eval_p1e(self, params) -> np.ndarray:
+        p = self._params(params)
+        shape = (len(p), 2 * self.n_etrue, self.n_paths) if self.col_major else (len(p), self.n_paths, 2 * self.n_etrue)
+        out = np.empty(shape)
+        self._check(self._L.solarosc_eval_p1e(self._h, _dp(p), len(p), _dp(out)))
+        return out
+
+    def eval_llh_device(self, d_params_ptr: int, n: int, d_lnl_ptr: int, d_flags_ptr: int = 0, group: int = 1,
+                        stream_ptr: int = 0):
+        """Enqueue on device-resident buffers (raw pointers, e.g. ``tensor.data_ptr()``); no synchronisation."""
+        self._check(self._L.solarosc_eval_llh_device(self._h, C.c_void_p(d_params_ptr), n, group, C.c_void_p(d_lnl_ptr),
+                                                     C.c_void_p(d_flags_ptr or None), C.c_void_p(stream_ptr or None)))
+
+    def poisson_llh(self, expected, measured):
+        e = np.ascontiguousarray(np.atleast_2d(expected), dtype=np.float64)
+        m = np.ascontiguousarray(np.atleast_2d(measured), dtype=np.float64)
+        if e.shape != m.shape:
+            raise ValueError("Inputs must have the same length")   # likelihood_statistical.jl:2-4
+        out = np.empty(len(e))
+        fl = np.zeros(len(e), dtype=np.uint32)
+        self._check(self._L.solarosc_poisson_llh(self._h, _dp(e), _dp(m), e.shape[0], e.shape[1], _dp(out),
+                                                 fl.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def last_timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        n = self._L.solarosc_last_timing(self._h, C.byref(a), C.byref(b))
+        return dict(ms_osc=a.value, ms_rates=b.value, launches=n)

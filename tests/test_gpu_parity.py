@@ -1,0 +1,214 @@
+"""GPU parity: CUDA path (through the C ABI) against the CPU oracle on identical tables.
+
+Tolerances are BASELINE.json's: per-bin rates <= 1e-9 relative, -2lnL <= 1e-6 absolute.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RATE_RTOL = 1e-9
+M2LNL_ATOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def engine(tables, asimov):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    with SolarOscEngine(tables, data=asimov) as e:
+        yield e
+
+
+@pytest.fixture(scope="module")
+def coracle(tables, asimov):
+    from oracle import oracle_c
+    return oracle_c.COracle(tables, asimov)
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_p1e_matches_oracle(engine, coracle, tables, draw):
+    p = draw(tables, 6, wide=True)
+    p[0] = tables["truth"]
+    got = engine.eval_p1e(p)
+    _, ref = coracle.eval_oscprobs(p, want_p1e=True)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) < 5e-12
+
+
+def test_vacuum_limit(engine, tables):
+    p = np.array(tables["truth"], dtype=np.float64)
+    p[8:14] = 0.0     # zero density in every layer: P1e = c12^2 c13^2 and night == day
+    p1e = engine.eval_p1e(p)
+    assert np.max(np.abs(p1e - (1 - p[0]) * (1 - p[1]))) < 1e-14
+    o = engine.eval_oscprobs(p)
+    assert np.max(np.abs(o["nue_8B_night"][0] - o["nue_8B_day"][0][None, :])) < 1e-14
+
+
+def test_oscprobs_match_oracle(engine, coracle, tables, draw):
+    p = draw(tables, 8)
+    got = engine.eval_oscprobs(p)
+    ref = coracle.eval_oscprobs(p)
+    assert np.max(np.abs(got["nue_8B_day"] - ref[:, 0, 0])) < 1e-14
+    assert np.max(np.abs(got["nue_hep_day"] - ref[:, 1, 0])) < 1e-14
+    assert np.max(np.abs(got["nue_8B_night"] - ref[:, 0, 1:])) < 5e-12
+    assert np.max(np.abs(got["nue_hep_night"] - ref[:, 1, 1:])) < 5e-12
+
+
+def test_rates_match_oracle(engine, coracle, tables, draw):
+    p = draw(tables, 16)
+    p[0] = tables["truth"]
+    got = engine.eval_rates(p)
+    ref = coracle.eval_rates(p)
+    for k in ("ES_day", "ES_night", "CC_day", "CC_night", "BG_ES_tot", "BG_CC_tot"):
+        assert got[k].shape == ref[k].shape, k
+        assert _rel(got[k], ref[k]) < RATE_RTOL, (k, _rel(got[k], ref[k]))
+
+
+def test_llh_matches_oracle(engine, coracle, tables, draw):
+    p = draw(tables, 96)
+    p[0] = tables["truth"]
+    got, fl = engine.eval_llh(p, return_flags=True)
+    ref, rfl = coracle.eval_llh(p)
+    assert np.array_equal(fl, rfl)
+    assert np.max(np.abs(-2 * got - (-2 * ref))) < M2LNL_ATOL
+    assert abs(got[0]) < 1e-6    # Asimov: lnL(truth) == 0 up to rounding
+
+
+def test_llh_numpy_twin_spot_check(engine, tables, asimov, draw):
+    from oracle import oracle_np
+    p = draw(tables, 3, seed=7)
+    got = engine.eval_llh(p)
+    ref = np.array([oracle_np.total_llh(q, tables, asimov) for q in p])
+    assert np.max(np.abs(2 * got - 2 * ref)) < M2LNL_ATOL
+
+
+def test_earth_norm_bounds_give_minus_inf(engine, tables):
+    p = np.tile(np.asarray(tables["truth"], dtype=np.float64), (3, 1))
+    p[1, 8] = -0.1
+    p[2, 10] = 2.1
+    got, fl = engine.eval_llh(p, return_flags=True)
+    assert np.isfinite(got[0]) and got[1] == -np.inf and got[2] == -np.inf
+    assert fl[1] == 1 and fl[2] == 1
+
+
+def test_grouped_equals_ungrouped(engine, tables, draw):
+    g = 9
+    p = draw(tables, 4 * g)
+    for c in range(4):    # a scan cell: oscillation columns constant, nuisances vary
+        p[c * g:(c + 1) * g, [0, 1, 2]] = p[c * g, [0, 1, 2]]
+        p[c * g:(c + 1) * g, 8:14] = p[c * g, 8:14]
+    a = engine.eval_llh(p)
+    b = engine.eval_llh(p, group=g)
+    assert np.array_equal(a, b)
+
+
+def test_chunking_and_determinism(tables, asimov, draw):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    p = draw(tables, 300)
+    with SolarOscEngine(tables, data=asimov, max_batch=64) as small, SolarOscEngine(tables, data=asimov) as big:
+        a, b, c = small.eval_llh(p), big.eval_llh(p), big.eval_llh(p)
+    assert np.array_equal(b, c)
+    # different batch sizes change the energy-chunking of the oscillation kernel but not the arithmetic
+    assert np.array_equal(a, b)
+
+
+def test_small_batches_use_energy_chunks(engine, coracle, tables, draw):
+    for n in (1, 2, 10):
+        p = draw(tables, n, seed=n)
+        ref, _ = coracle.eval_llh(p)
+        assert np.max(np.abs(2 * engine.eval_llh(p) - 2 * ref)) < M2LNL_ATOL
+
+
+def test_perbin_matches_oracle(engine, tables, asimov, draw):
+    from oracle import oracle_np
+    p = draw(tables, 2, seed=3)
+    p[1, 9] = 2.5
+    got = engine.eval_perbin(p)
+    for i in range(2):
+        ref = oracle_np.perbin_llh(p[i], tables, asimov)
+        for k in ("ES_day", "ES_night", "CC_day", "CC_night"):
+            if i == 1:
+                assert np.all(got[k][i] == -np.inf)
+            else:
+                scale = np.maximum(np.abs(ref[k]), 1.0)
+                assert np.max(np.abs(got[k][i] - ref[k]) / scale) < 1e-9, k
+
+
+def test_slow_mode_matches_oracle(tables, draw):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    from oracle import oracle_c, oracle_np
+    data = oracle_np.asimov_data(tables, fast=False)
+    p = draw(tables, 4)
+    ref_o = oracle_c.COracle(tables, data, fast=False)
+    with SolarOscEngine(tables, data=data, fast=False) as e:
+        got = e.eval_oscprobs(p)
+        ref = ref_o.eval_oscprobs(p)
+        assert np.max(np.abs(got["nue_8B_day"] - ref[:, 0, 0])) < 1e-13
+        assert np.max(np.abs(got["nue_8B_night"] - ref[:, 0, 1:])) < 5e-12
+        lr, _ = ref_o.eval_llh(p)
+        assert np.max(np.abs(2 * e.eval_llh(p) - 2 * lr)) < M2LNL_ATOL
+
+
+def test_col_major_layout(tables, asimov, draw):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    p = draw(tables, 3)
+    t2 = dict(tables)
+    for k in ("resp_es_nue", "resp_es_nuother", "resp_cc"):
+        t2[k] = np.ascontiguousarray(tables[k].T)   # a numpy view of Julia's column-major memory
+    d2 = {k: (np.ascontiguousarray(v.T) if v.ndim == 2 else v) for k, v in asimov.items()}
+    with SolarOscEngine(tables, data=asimov) as a, SolarOscEngine(t2, data=d2, col_major=True) as b:
+        ra, rb = a.eval_rates(p), b.eval_rates(p)
+        assert np.array_equal(a.eval_llh(p), b.eval_llh(p))
+        assert np.array_equal(ra["ES_night"], rb["ES_night"].transpose(0, 2, 1))
+        assert np.array_equal(ra["CC_night"], rb["CC_night"].transpose(0, 2, 1))
+        assert np.array_equal(a.eval_p1e(p), b.eval_p1e(p).transpose(0, 2, 1))
+
+
+def test_poisson_kats(engine):
+    # reference tests/test_likelihood_correctness.jl:5-17
+    e = np.array([10.0, 20.0, 30.0, 15.0]); m = np.array([12.0, 18.0, 29.0, 14.0])
+    ref = np.sum((e - m) + m * np.log(m / e))
+    assert abs(engine.poisson_llh(e, m)[0] + ref) < 1e-10
+    n = np.array([1.0, 5.0, 10.0])
+    assert abs(engine.poisson_llh(n, n)[0]) < 1e-12
+    assert np.isfinite(engine.poisson_llh([0.0, 1.0, 2.0], [0.0, 0.0, 3.0])[0])
+    with pytest.raises(ValueError):
+        engine.poisson_llh([1.0, 2.0], [1.0])
+
+
+def test_poisson_benchmark_shape(engine):
+    # reference tests/benchmark_likelihoods.jl:10-19: two length-10000 vectors of U{10..50}
+    from oracle import oracle_c
+    rng = np.random.default_rng(5)
+    e = rng.integers(10, 51, (4, 10000)).astype(float); m = rng.integers(10, 51, (4, 10000)).astype(float)
+    got = engine.poisson_llh(e, m)
+    ref = np.array([oracle_c.COracle.poisson(e[i], m[i])[0] for i in range(4)])
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+
+
+def test_negative_rate_flags(tables, asimov):
+    from dune_solaroscfitter_b200 import abi
+    from dune_solaroscfitter_b200.engine import NegativeRateError, SolarOscEngine
+    p = np.array(tables["truth"], dtype=np.float64)
+    p[-5:] = -2.2e-6    # negative background norms: expected rates far below -1e-3
+    with SolarOscEngine(tables, data=asimov) as e:
+        got, fl = e.eval_llh(p, return_flags=True)
+        assert np.isnan(got[0]) and fl[0] & abi.FLAG_NEG_ERROR
+        with pytest.raises(NegativeRateError):
+            e.eval_llh(p, raise_on_negative=True)
+
+
+def test_device_resident_entry(engine, tables, draw):
+    torch = pytest.importorskip("torch")
+    p = draw(tables, 513)
+    ref = engine.eval_llh(p)
+    dp = torch.from_numpy(p).cuda()
+    out = torch.empty(len(p), dtype=torch.float64, device="cuda")
+    fl = torch.zeros(len(p), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    engine.eval_llh_device(dp.data_ptr(), len(p), out.data_ptr(), fl.data_ptr(),
+                           stream_ptr=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
