@@ -13,7 +13,7 @@ from . import abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libsolarosc_b200.so")
+LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
 _SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
@@ -21,7 +21,7 @@ EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
     "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_rates",
     "solarosc_eval_perbin", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
-    "solarosc_poisson_llh", "solarosc_last_timing",
+    "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_measure_fp64_peak",
 )
 
 _lib = None
@@ -69,6 +69,8 @@ def load():
     L.solarosc_eval_p1e.argtypes = [H, dp, sz, dp]
     L.solarosc_eval_llh_device.argtypes = [H, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, C.c_void_p]
     L.solarosc_poisson_llh.argtypes = [H, dp, dp, sz, sz, dp, up]
+    L.solarosc_set_timing.argtypes = [H, C.c_int]
     L.solarosc_last_timing.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.solarosc_measure_fp64_peak.argtypes = [H, dp]
     _lib = L
     return L

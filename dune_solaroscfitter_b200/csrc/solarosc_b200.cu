@@ -51,20 +51,25 @@ struct solarosc_handle {
     int device = 0, sm_count = 148, chunk = 4096, P = 0;
     int max_ereco = 0;
     int n_es[kMaxDet]{}, n_cc[kMaxDet]{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[3]{};
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D / D2H of the host-buffer pipeline
+    cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{};
+    std::vector<cudaEvent_t> tev;        // timing events, three per chunk (before osc, between, after rates)
+    size_t tev_used = 0;
+    cudaStream_t tev_stream = nullptr;
+    bool timing = false;
     std::vector<void*> dev_allocs;
     // per-detector data buffers (device, [1+n_cosz][n_ereco]) kept so set_data can overwrite them
     double *d_obs_es[kMaxDet]{}, *d_obs_cc[kMaxDet]{}, *d_log_es[kMaxDet]{}, *d_log_cc[kMaxDet]{};
     bool has_data[kMaxDet]{};
     // workspaces
-    double* d_params = nullptr;
+    double* d_params2[2]{};      // double-buffered parameter chunks
+    double* d_params = nullptr;  // == d_params2[0]
     double* d_osc = nullptr;
-    double* d_lnl = nullptr;
-    uint32_t* d_flags = nullptr;
-    double* h_params = nullptr;  // pinned
-    double* h_lnl = nullptr;     // pinned
-    uint32_t* h_flags = nullptr; // pinned
+    double* d_lnl2[2]{};
+    uint32_t* d_flags2[2]{};
+    uint32_t* h_flags = nullptr; // pinned, grown on demand (n_points)
+    size_t h_flags_n = 0;
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
     size_t scratch_bytes = 0;
     size_t osc_smem_limit = 200 * 1024;
@@ -87,6 +92,14 @@ struct solarosc_handle {
         return d;
     }
     double* upload_vec(const std::vector<double>& v) { return upload(v.data(), v.size()); }
+    cudaEvent_t next_tev() {
+        if (tev_used == tev.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            tev.push_back(e);
+        }
+        return tev[tev_used++];
+    }
     void ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return;
         if (d_scratch) CK(cudaFree(d_scratch));
@@ -99,9 +112,9 @@ struct solarosc_handle {
 
 namespace {
 
-// [a][b] table given in either layout -> row-major copy (b fastest)
-std::vector<double> to_row_major(const double* src, int na, int nb, bool col_major) {
-    std::vector<double> out((size_t)na * nb);
+// [a][b] table given in either layout -> row-major copy (b fastest), zero-padded to na_pad rows
+std::vector<double> to_row_major(const double* src, int na, int nb, bool col_major, int na_pad = 0) {
+    std::vector<double> out((size_t)std::max(na, na_pad) * nb, 0.0);
     for (int a = 0; a < na; ++a)
         for (int b = 0; b < nb; ++b) out[(size_t)a * nb + b] = col_major ? src[(size_t)b * na + a] : src[(size_t)a * nb + b];
     return out;
@@ -147,7 +160,13 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     h->sm_count = prop.multiProcessorCount;
     h->osc_smem_limit = std::min<size_t>(200 * 1024, prop.sharedMemPerBlockOptin);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (auto& e : h->ev) CK(cudaEventCreate(&e));
+    CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
 
     DevTables& T = h->T;
     T.n_etrue = t->n_etrue; T.n_e = 2 * t->n_etrue; T.n_cosz = t->n_cosz; T.n_sub = t->n_cosz_sub;
@@ -216,9 +235,9 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         D.u_cc_8b = h->upload(s.unosc_cc_8b, nT); D.u_es_nue_hep = h->upload(s.unosc_es_nue_hep, nT);
         D.u_es_nuo_hep = h->upload(s.unosc_es_nuother_hep, nT); D.u_cc_hep = h->upload(s.unosc_cc_hep, nT);
         D.log_e_norm = h->upload(s.log_e_norm, nT);
-        D.r_es_nue = h->upload_vec(to_row_major(s.resp_es_nue, nT, D.n_es, cm));
-        D.r_es_nuo = h->upload_vec(to_row_major(s.resp_es_nuother, nT, D.n_es, cm));
-        D.r_cc = h->upload_vec(to_row_major(s.resp_cc, nT, D.n_cc, cm));
+        D.r_es_nue = h->upload_vec(to_row_major(s.resp_es_nue, nT, D.n_es, cm, (nT + 1) & ~1));
+        D.r_es_nuo = h->upload_vec(to_row_major(s.resp_es_nuother, nT, D.n_es, cm, (nT + 1) & ~1));
+        D.r_cc = h->upload_vec(to_row_major(s.resp_cc, nT, D.n_cc, cm, (nT + 1) & ~1));
         D.eff_es_nue = h->upload(s.eff_es_nue, D.n_es); D.eff_es_nuo = h->upload(s.eff_es_nuother, D.n_es);
         D.eff_cc = h->upload(s.eff_cc, D.n_cc);
         D.raw_bg_es = h->upload(s.raw_bg_es, (size_t)D.n_bg_es * D.n_es);
@@ -246,18 +265,22 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     }
     h->P = off;
     T.n_params = off;
-    h->chunk = c->max_batch > 0 ? c->max_batch : 4096;
     const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
-    h->d_params = h->dalloc<double>((size_t)h->chunk * h->P);
+    // Points per internal chunk.  The oscillation-probability workspace (osc_pt doubles per point)
+    // is the only large buffer; the default keeps it near 1 GiB of the 180 GB of HBM.
+    h->chunk = c->max_batch > 0 ? c->max_batch : (int)std::max<size_t>(1024, std::min<size_t>(32768, ((size_t)1 << 30) / (osc_pt * sizeof(double))));
+    for (int i = 0; i < 2; ++i) {
+        h->d_params2[i] = h->dalloc<double>((size_t)h->chunk * h->P);
+        h->d_lnl2[i] = h->dalloc<double>(h->chunk);
+        h->d_flags2[i] = h->dalloc<uint32_t>(h->chunk);
+    }
+    h->d_params = h->d_params2[0];
     h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
-    h->d_lnl = h->dalloc<double>(h->chunk);
-    h->d_flags = h->dalloc<uint32_t>(h->chunk);
-    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_params), (size_t)h->chunk * h->P * sizeof(double)));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_lnl), (size_t)h->chunk * sizeof(double)));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), (size_t)h->chunk * sizeof(uint32_t)));
     const size_t rs = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
     if (rs > prop.sharedMemPerBlockOptin) throw ArgFail{"binning too large for the rate kernel's shared-memory tile"};
-    CK(cudaFuncSetAttribute(rates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    CK(cudaFuncSetAttribute(rates_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
 }
 
@@ -288,7 +311,11 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     const bool cm = h->cfg.col_major != 0;
     L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? T.n_cosz : 1;
     L.s_row_cc = cm ? 1 : h->n_cc[d]; L.s_j_cc = cm ? T.n_cosz : 1;
-    rates_kernel<<<n, kRatesThreads, rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco), st>>>(T, L, d_params, h->d_osc, O);
+    L.max_ereco = h->max_ereco;
+    const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    else rates_kernel<kModePerbin><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     CK(cudaGetLastError());
     ++h->launches;
 }
@@ -321,38 +348,52 @@ int guarded(solarosc_handle* h, F&& body) {
     }
 }
 
-// Host-buffer likelihood evaluation, chunked.
+// Host-buffer likelihood evaluation.  Three streams form a pipeline over chunks: H2D of chunk c+1
+// (straight from the caller's buffer: asynchronous when it is pinned, staged by the driver when
+// pageable) overlaps the two kernels of chunk c and the D2H of chunk c-1; the host thread only
+// enqueues and synchronises once at the end.
 int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t group, double* out, uint32_t* flags) {
     REQUIRE(params && out, "params and out_lnl must not be NULL");
     REQUIRE(group >= 1 && n % group == 0, "n_points must be a multiple of group");
     REQUIRE(group <= (size_t)h->chunk, "group larger than max_batch");
     check_data(h, -1);
-    h->ms_osc = h->ms_rates = 0.f;
     h->launches = 0;
-    const size_t step = ((size_t)h->chunk / group) * group;
-    bool neg = false;
-    for (size_t b0 = 0; b0 < n; b0 += step) {
-        const int nb = (int)std::min(step, n - b0);
-        std::memcpy(h->h_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double));
-        CK(cudaMemcpyAsync(h->d_params, h->h_params, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaEventRecord(h->ev[0], h->stream));
-        launch_osc(h, h->d_params, nb / (int)group, (int)group, nullptr, h->stream);
-        CK(cudaEventRecord(h->ev[1], h->stream));
-        RatesOut O{};
-        O.lnl = h->d_lnl; O.flags = h->d_flags;
-        launch_rates(h, h->d_params, nb, (int)group, kModeLlh, -1, O, h->stream);
-        CK(cudaEventRecord(h->ev[2], h->stream));
-        CK(cudaMemcpyAsync(h->h_lnl, h->d_lnl, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_flags, h->d_flags, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        float a = 0.f, c = 0.f;
-        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-        CK(cudaEventElapsedTime(&c, h->ev[1], h->ev[2]));
-        h->ms_osc += a; h->ms_rates += c;
-        std::memcpy(out + b0, h->h_lnl, nb * sizeof(double));
-        if (flags) std::memcpy(flags + b0, h->h_flags, nb * sizeof(uint32_t));
-        for (int i = 0; i < nb; ++i) neg |= (h->h_flags[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+    h->tev_used = 0;
+    h->tev_stream = h->stream;
+    if (n > h->h_flags_n) {
+        if (h->h_flags) CK(cudaFreeHost(h->h_flags));
+        h->h_flags = nullptr; h->h_flags_n = 0;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), n * sizeof(uint32_t)));
+        h->h_flags_n = n;
     }
+    const size_t step = ((size_t)h->chunk / group) * group;
+    size_t c = 0;
+    for (size_t b0 = 0; b0 < n; b0 += step, ++c) {
+        const int nb = (int)std::min(step, n - b0);
+        const int slot = (int)(c & 1);
+        if (c >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 have read this slot
+        CK(cudaMemcpyAsync(h->d_params2[slot], params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+        CK(cudaEventRecord(h->ev_in[slot], h->s_in));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));  // results of chunk c-2 have left this slot
+        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
+        launch_osc(h, h->d_params2[slot], nb / (int)group, (int)group, nullptr, h->stream);
+        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
+        RatesOut O{};
+        O.lnl = h->d_lnl2[slot]; O.flags = h->d_flags2[slot];
+        launch_rates(h, h->d_params2[slot], nb, (int)group, kModeLlh, -1, O, h->stream);
+        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
+        CK(cudaEventRecord(h->ev_done[slot], h->stream));
+        CK(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+        CK(cudaMemcpyAsync(out + b0, h->d_lnl2[slot], nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaMemcpyAsync(h->h_flags + b0, h->d_flags2[slot], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaEventRecord(h->ev_out[slot], h->s_out));
+    }
+    CK(cudaStreamSynchronize(h->s_out));
+    CK(cudaStreamSynchronize(h->stream));
+    bool neg = false;
+    for (size_t i = 0; i < n; ++i) neg |= (h->h_flags[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+    if (flags) std::memcpy(flags, h->h_flags, n * sizeof(uint32_t));
     if (neg) {
         h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
         return SOLAROSC_ERR_NEGATIVE_RATE;
@@ -373,8 +414,7 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     h->launches = 0;
     for (size_t b0 = 0; b0 < n; b0 += step) {
         const int nb = (int)std::min<size_t>(step, n - b0);
-        std::memcpy(h->h_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double));
-        CK(cudaMemcpyAsync(h->d_params, h->h_params, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
         double* s = h->d_scratch;
         RatesOut O{};
@@ -440,14 +480,18 @@ solarosc_handle* solarosc_create(const solarosc_tables* tables, const solarosc_c
 void solarosc_destroy(solarosc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->d_scratch) cudaFree(h->d_scratch);
-    if (h->h_params) cudaFreeHost(h->h_params);
-    if (h->h_lnl) cudaFreeHost(h->h_lnl);
     if (h->h_flags) cudaFreeHost(h->h_flags);
-    for (auto& e : h->ev)
-        if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    for (auto& e : h->tev) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -555,13 +599,18 @@ int solarosc_eval_llh_device(solarosc_handle* h, const double* d_params, size_t 
         cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
         const size_t step = ((size_t)h->chunk / group) * group;
         h->launches = 0;
+        h->tev_used = 0;
+        h->tev_stream = st;
         for (size_t b0 = 0; b0 < n; b0 += step) {
             const int nb = (int)std::min(step, n - b0);
+            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
             launch_osc(h, d_params + b0 * h->P, nb / (int)group, (int)group, nullptr, st);
+            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
             RatesOut O{};
             O.lnl = d_lnl + b0;
             O.flags = d_flags ? d_flags + b0 : nullptr;
             launch_rates(h, d_params + b0 * h->P, nb, (int)group, kModeLlh, -1, O, st);
+            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
         }
         return (int)SOLAROSC_OK;
     });
@@ -596,11 +645,57 @@ int solarosc_poisson_llh(solarosc_handle* h, const double* expected, const doubl
     });
 }
 
-int solarosc_last_timing(const solarosc_handle* h, float* ms_osc, float* ms_rates) {
+int solarosc_set_timing(solarosc_handle* h, int enabled) {
+    if (!h) return SOLAROSC_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->timing = enabled != 0;
+    return SOLAROSC_OK;
+}
+
+int solarosc_last_timing(solarosc_handle* h, float* ms_osc, float* ms_rates) {
     if (!h) return -1;
-    if (ms_osc) *ms_osc = h->ms_osc;
-    if (ms_rates) *ms_rates = h->ms_rates;
+    std::lock_guard<std::mutex> lk(h->mu);
+    float a = 0.f, c = 0.f;
+    if (h->timing && h->tev_used >= 3) {
+        cudaSetDevice(h->device);
+        if (cudaEventSynchronize(h->tev[h->tev_used - 1]) == cudaSuccess)
+            for (size_t i = 0; i + 2 < h->tev_used; i += 3) {
+                float x = 0.f, y = 0.f;
+                cudaEventElapsedTime(&x, h->tev[i], h->tev[i + 1]);
+                cudaEventElapsedTime(&y, h->tev[i + 1], h->tev[i + 2]);
+                a += x; c += y;
+            }
+    }
+    if (ms_osc) *ms_osc = a;
+    if (ms_rates) *ms_rates = c;
     return h->launches;
+}
+
+int solarosc_measure_fp64_peak(solarosc_handle* h, double* tflops) {
+    return guarded(h, [&]() {
+        REQUIRE(tflops, "NULL pointer");
+        double* d = nullptr;
+        CK(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(double) * 1024));
+        const int iters = 1 << 14, blocks = h->sm_count * 8, threads = 256;
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; ++rep) {
+            CK(cudaEventRecord(e0, h->stream));
+            dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters, 1.0000001);
+            CK(cudaEventRecord(e1, h->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        CK(cudaGetLastError());
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CK(cudaFree(d));
+        const double fl = 2.0 * 16.0 * (double)iters * blocks * threads;   // 16 independent FMA chains per thread
+        *tflops = fl / (best * 1e-3) * 1e-12;
+        return (int)SOLAROSC_OK;
+    });
 }
 
 }  // extern "C"

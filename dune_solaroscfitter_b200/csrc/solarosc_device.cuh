@@ -57,48 +57,64 @@ struct DevTables {
 // CUDA's sincos(), which also carries a Payne-Hanek slow path these phases can never take.
 // The largest phase of the default configuration is c*L*dm31/E ~ 7e4 rad.
 // ------------------------------------------------------------------------------------------
+// Coefficients of the reduction and of the fdlibm sin/cos minimax kernels.  On the device they live
+// in constant memory so that every DFMA takes its coefficient as a constant-bank operand (literal
+// doubles are otherwise rebuilt with two UMOVs per use).
+#define SOLAROSC_TRIG_TABLE                                                                           \
+    6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17,               \
+        1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,          \
+        -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,         \
+        -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,         \
+        2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, 0.0
+static __constant__ double kTrigDev[16] = {SOLAROSC_TRIG_TABLE};
+static const double kTrigHost[16] = {SOLAROSC_TRIG_TABLE};
+
 #if defined(__CUDA_ARCH__)
 #define SOLAROSC_HD __host__ __device__ __forceinline__
+#define SOLAROSC_TRIG(i) kTrigDev[i]
 __device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
 __device__ __forceinline__ int lo_int(double x) { return __double2loint(x); }
+// x with its sign flipped when `flip` has bit 31 set: an integer XOR, not an FP64-pipe negation
+__device__ __forceinline__ double flip_sign(double x, int flip) {
+    return __hiloint2double(__double2hiint(x) ^ (flip & 0x80000000), __double2loint(x));
+}
 #else
 // The same helpers compile for the host so that tests can run the exact kernel arithmetic on the
 // CPU (tests/csrc/host_math_check.cu); the library itself never executes them there.
 #define SOLAROSC_HD __host__ __device__ inline
+#define SOLAROSC_TRIG(i) kTrigHost[i]
 inline double rsq(double x) { return 1.0 / std::sqrt(x); }
 inline int lo_int(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
+inline double flip_sign(double x, int flip) { return (flip & 0x80000000) ? -x : x; }
 #endif
 
 SOLAROSC_HD void sincos_phase(double x, double& s, double& c) {
-    const double kTwoOverPi = 6.36619772367581382433e-01;
-    const double kPio2Hi = 1.57079632679489655800e+00;
-    const double kPio2Lo = 6.12323399573676603587e-17;
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: forces round-to-nearest-integer
-    double kd = fma(x, kTwoOverPi, kMagic);
-    int q = lo_int(kd);
+    double kd = fma(x, SOLAROSC_TRIG(0), kMagic);
+    const int q = lo_int(kd);
     kd -= kMagic;
-    double r = fma(-kd, kPio2Hi, x);
-    r = fma(-kd, kPio2Lo, r);
-    double z = r * r;
+    double r = fma(-kd, SOLAROSC_TRIG(1), x);
+    r = fma(-kd, SOLAROSC_TRIG(2), r);
+    const double z = r * r;
     // sin kernel
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    double sr = fma(z * r, ps, r);
+    double ps = fma(z, SOLAROSC_TRIG(3), SOLAROSC_TRIG(4));
+    ps = fma(z, ps, SOLAROSC_TRIG(5));
+    ps = fma(z, ps, SOLAROSC_TRIG(6));
+    ps = fma(z, ps, SOLAROSC_TRIG(7));
+    ps = fma(z, ps, SOLAROSC_TRIG(8));
+    const double sr = fma(z * r, ps, r);
     // cos kernel
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-    // quadrant: q mod 4 = 0: (s,c)=(sr,cr) 1: (cr,-sr) 2: (-sr,-cr) 3: (-cr,sr)
-    double ss = (q & 1) ? cr : sr;
-    double cc = (q & 1) ? sr : cr;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cc : cc;
+    double pc = fma(z, SOLAROSC_TRIG(9), SOLAROSC_TRIG(10));
+    pc = fma(z, pc, SOLAROSC_TRIG(11));
+    pc = fma(z, pc, SOLAROSC_TRIG(12));
+    pc = fma(z, pc, SOLAROSC_TRIG(13));
+    pc = fma(z, pc, SOLAROSC_TRIG(14));
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant q mod 4: 0 (sr, cr)   1 (cr, -sr)   2 (-sr, -cr)   3 (-cr, sr)
+    const double ss = (q & 1) ? cr : sr;
+    const double cc = (q & 1) ? sr : cr;
+    s = flip_sign(ss, q << 30);          // bit 1 of q -> sign bit
+    c = flip_sign(cc, (q + 1) << 30);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -111,13 +127,13 @@ SOLAROSC_HD void sincos_phase(double x, double& s, double& c) {
 //     S = diag(0, dm21, dm31) + a * u u^T  - a*I,     a = rho*E,  u = (c12 c13, s12 c13, s13),
 // and P1e = |<nu_1| prod_k exp(-i S_k t_k) |u>|^2 does not depend on theta23 or deltaCP at all.
 // S is a rank-one update of a diagonal matrix: eigenvalues from the trigonometric solution of the
-// characteristic cubic, eigenvectors from v_i[j] ~ u_j * prod_{k != j} (mu_i - m_k) (no
-// divisions, well defined when a or some u_j vanish).  Only eigenvalue differences are
-// returned (the common phase drops out of |amplitude|^2).
+// characteristic cubic, refined through the secular equation; eigenvectors from
+// v_i[j] ~ u_j * prod_{k != j} (mu_i - m_k) (no divisions, well defined when a or some u_j
+// vanish).  Only eigenvalue differences are returned (the common phase drops out of |amplitude|^2).
 // q[3*j+i] = component j of eigenvector i.
 // ------------------------------------------------------------------------------------------
 SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, double u2, double u3,
-                                             double q[9], double& w2, double& w3) {
+                              double q[9], double& w2, double& w3) {
     const double m[3] = {0.0, d21, d31};
     const double u[3] = {u1, u2, u3};
     double s11 = a * u1 * u1, s22 = fma(a * u2, u2, d21), s33 = fma(a * u3, u3, d31);
@@ -179,27 +195,92 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
     w3 = (m[2] - m[0]) + (dl[2] - dl[0]);
 }
 
-// One constant-density step of the state vector in the vacuum mass basis:
-//   psi <- Q diag(1, e^{-i phi2}, e^{-i phi3}) Q^T psi      (reference osc_kernel, osc.jl:360-364,
-// applied to a vector instead of forming the 3x3 product of osc.jl:442; 44 FMA-pipe operations and
-// two sincos instead of ~400 flops and three complex exponentials).  e points at this (energy,
-// layer) entry of the eigen table, cs is the stride between its 11 components.
-SOLAROSC_HD void earth_step(const double* e, size_t cs, double len, double& ar, double& ai, double& br, double& bi,
-                            double& cr, double& ci) {
-    const double q00 = e[0], q01 = e[cs], q02 = e[2 * cs];
-    const double q10 = e[3 * cs], q11 = e[4 * cs], q12 = e[5 * cs];
-    const double q20 = e[6 * cs], q21 = e[7 * cs], q22 = e[8 * cs];
-    double s2, c2, s3, c3;
-    sincos_phase(len * e[9 * cs], s2, c2);
-    sincos_phase(len * e[10 * cs], s3, c3);
-    const double w0r = fma(q20, cr, fma(q10, br, q00 * ar)), w0i = fma(q20, ci, fma(q10, bi, q00 * ai));
-    const double w1r = fma(q21, cr, fma(q11, br, q01 * ar)), w1i = fma(q21, ci, fma(q11, bi, q01 * ai));
-    const double w2r = fma(q22, cr, fma(q12, br, q02 * ar)), w2i = fma(q22, ci, fma(q12, bi, q02 * ai));
-    const double x1r = fma(w1i, s2, w1r * c2), x1i = fma(-w1r, s2, w1i * c2);
-    const double x2r = fma(w2i, s3, w2r * c3), x2i = fma(-w2r, s3, w2i * c3);
-    ar = fma(q02, x2r, fma(q01, x1r, q00 * w0r)); ai = fma(q02, x2i, fma(q01, x1i, q00 * w0i));
-    br = fma(q12, x2r, fma(q11, x1r, q10 * w0r)); bi = fma(q12, x2i, fma(q11, x1i, q10 * w0i));
-    cr = fma(q22, x2r, fma(q21, x1r, q20 * w0r)); ci = fma(q22, x2i, fma(q21, x1i, q20 * w0i));
+// ------------------------------------------------------------------------------------------
+// Eigen table entry of one (layer, fine energy): what the propagation loop needs and nothing else.
+// With eigenvectors q_0, q_1, q_2 (q_0 belongs to the lowest eigenvalue) one constant-density step is
+//     psi <- Q diag(1, e^{-i phi_1}, e^{-i phi_2}) Q^T psi = psi + sum_{n=1,2} q_n (e^{-i phi_n} - 1) (q_n . psi),
+// so q_0 and the common phase are never needed (reference osc_kernel, osc.jl:360-364, applied to a
+// vector instead of forming the 3x3 products of osc.jl:442).
+//   [0..2] q_1   [3..5] q_2   [6] c*(mu_1-mu_0)/E   [7] c*(mu_2-mu_0)/E   [8] q_1.u   [9] q_2.u
+// The stride of 11 doubles keeps the per-lane 8-byte loads of consecutive energies bank-conflict free.
+// ------------------------------------------------------------------------------------------
+constexpr int kEntry = 11;
+
+SOLAROSC_HD void make_entry(double dm21, double a, double e_gev, double u1, double u2, double u3, double* ent) {
+    double q[9], w2, w3;
+    eig_rank_one(dm21, kDm31, a, u1, u2, u3, q, w2, w3);
+    const double f = kPhase / e_gev;   // phase = 2.5338653580781976 * (l/e) * lambda  (osc.jl:361)
+    ent[0] = q[1]; ent[1] = q[4]; ent[2] = q[7];
+    ent[3] = q[2]; ent[4] = q[5]; ent[5] = q[8];
+    ent[6] = f * w2; ent[7] = f * w3;
+    ent[8] = fma(q[7], u3, fma(q[4], u2, q[1] * u1));
+    ent[9] = fma(q[8], u3, fma(q[5], u2, q[2] * u1));
+    ent[10] = 0.0;
+}
+
+struct State { double ar, ai, br, bi, cr, ci; };
+
+// y_n = e^{-i phi_n} - 1 for both excited eigenstates of this entry
+SOLAROSC_HD void step_phases(const double* e, double len, double& y1r, double& y1i, double& y2r, double& y2i) {
+    double s1, c1, s2, c2;
+    sincos_phase(len * e[6], s1, c1);
+    sincos_phase(len * e[7], s2, c2);
+    y1r = c1 - 1.0; y1i = -s1; y2r = c2 - 1.0; y2i = -s2;
+}
+
+// first step of a path: psi = u is real, q_n.u is tabulated
+SOLAROSC_HD void step_first(const double* e, double len, double u1, double u2, double u3, State& p) {
+    double y1r, y1i, y2r, y2i;
+    step_phases(e, len, y1r, y1i, y2r, y2i);
+    const double t1r = y1r * e[8], t1i = y1i * e[8], t2r = y2r * e[9], t2i = y2i * e[9];
+    p.ar = fma(e[3], t2r, fma(e[0], t1r, u1)); p.ai = fma(e[3], t2i, e[0] * t1i);
+    p.br = fma(e[4], t2r, fma(e[1], t1r, u2)); p.bi = fma(e[4], t2i, e[1] * t1i);
+    p.cr = fma(e[5], t2r, fma(e[2], t1r, u3)); p.ci = fma(e[5], t2i, e[2] * t1i);
+}
+
+// t_n = y_n * (q_n . psi)
+SOLAROSC_HD void step_project(const double* e, double len, const State& p, double& t1r, double& t1i, double& t2r,
+                              double& t2i) {
+    double y1r, y1i, y2r, y2i;
+    step_phases(e, len, y1r, y1i, y2r, y2i);
+    const double w1r = fma(e[2], p.cr, fma(e[1], p.br, e[0] * p.ar)), w1i = fma(e[2], p.ci, fma(e[1], p.bi, e[0] * p.ai));
+    const double w2r = fma(e[5], p.cr, fma(e[4], p.br, e[3] * p.ar)), w2i = fma(e[5], p.ci, fma(e[4], p.bi, e[3] * p.ai));
+    t1r = fma(-y1i, w1i, y1r * w1r); t1i = fma(y1i, w1r, y1r * w1i);
+    t2r = fma(-y2i, w2i, y2r * w2r); t2i = fma(y2i, w2r, y2r * w2i);
+}
+
+SOLAROSC_HD void step_mid(const double* e, double len, State& p) {
+    double t1r, t1i, t2r, t2i;
+    step_project(e, len, p, t1r, t1i, t2r, t2i);
+    p.ar = fma(e[3], t2r, fma(e[0], t1r, p.ar)); p.ai = fma(e[3], t2i, fma(e[0], t1i, p.ai));
+    p.br = fma(e[4], t2r, fma(e[1], t1r, p.br)); p.bi = fma(e[4], t2i, fma(e[1], t1i, p.bi));
+    p.cr = fma(e[5], t2r, fma(e[2], t1r, p.cr)); p.ci = fma(e[5], t2i, fma(e[2], t1i, p.ci));
+}
+
+// last step: only the nu_1 component of the state is read afterwards
+SOLAROSC_HD void step_last(const double* e, double len, State& p) {
+    double t1r, t1i, t2r, t2i;
+    step_project(e, len, p, t1r, t1i, t2r, t2i);
+    p.ar = fma(e[3], t2r, fma(e[0], t1r, p.ar)); p.ai = fma(e[3], t2i, fma(e[0], t1i, p.ai));
+}
+
+// P(nu_1 -> nu_e) of one path at one energy.  tbl points at the entry of layer 0 for this energy,
+// layer_stride is the distance in doubles between the entries of consecutive layers.
+SOLAROSC_HD double path_p1e(const double* tbl, size_t layer_stride, const int* app_layer, const double* app_len, int s0,
+                            int s1, double u1, double u2, double u3) {
+    State p;
+    const double* e = tbl + (size_t)app_layer[s0] * layer_stride;
+    if (s1 - s0 == 1) {   // one layer: first and last step at once
+        double y1r, y1i, y2r, y2i;
+        step_phases(e, app_len[s0], y1r, y1i, y2r, y2i);
+        const double t1r = y1r * e[8], t1i = y1i * e[8], t2r = y2r * e[9], t2i = y2i * e[9];
+        p.ar = fma(e[3], t2r, fma(e[0], t1r, u1)); p.ai = fma(e[3], t2i, e[0] * t1i);
+    } else {
+        step_first(e, app_len[s0], u1, u2, u3, p);
+        for (int s = s0 + 1; s < s1 - 1; ++s) step_mid(tbl + (size_t)app_layer[s] * layer_stride, app_len[s], p);
+        step_last(tbl + (size_t)app_layer[s1 - 1] * layer_stride, app_len[s1 - 1], p);
+    }
+    return fma(p.ar, p.ar, p.ai * p.ai);   // |<nu_1|X|nu_e>|^2 (osc.jl:444)
 }
 
 // MSW survival probability pieces (reference osc.jl:77-90): returns cos(2 theta12_matter)

@@ -157,6 +157,14 @@ class SolarOscEngine:
                                                  fl.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def set_timing(self, enabled: bool = True):
+        self._check(self._L.solarosc_set_timing(self._h, int(enabled)))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0)
+        self._check(self._L.solarosc_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     def last_timing(self):
         a, b = C.c_float(0), C.c_float(0)
         n = self._L.solarosc_last_timing(self._h, C.byref(a), C.byref(b))

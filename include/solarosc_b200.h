@@ -190,9 +190,17 @@ int solarosc_eval_llh_device(solarosc_handle *h, const double *d_params, size_t 
 int solarosc_poisson_llh(solarosc_handle *h, const double *expected, const double *measured, size_t n_vec,
                          size_t len, double *out, uint32_t *out_flags);
 
-/* Device time of the kernels of the last eval call on this handle, in milliseconds (CUDA events on
- * the launching stream): oscillation stage, rate+likelihood stage.  Returns the launch count. */
-int solarosc_last_timing(const solarosc_handle *h, float *ms_osc, float *ms_rates);
+/* Per-kernel device timing.  When enabled, eval_llh / eval_llh_grouped / eval_llh_device record CUDA
+ * events around each kernel on the launching stream; solarosc_last_timing waits for the last one and
+ * returns the summed durations [ms] of the oscillation kernel and of the rate+likelihood kernel of
+ * the last such call.  Its return value is the number of kernels that call launched (always
+ * counted, timing or not). */
+int solarosc_set_timing(solarosc_handle *h, int enabled);
+int solarosc_last_timing(solarosc_handle *h, float *ms_osc, float *ms_rates);
+
+/* Measured FP64 FMA throughput of the handle's device in TFLOP/s (dependent-chain DFMA probe): the
+ * denominator of the FP64 roofline, which MEASURED_PEAKS.json does not carry. */
+int solarosc_measure_fp64_peak(solarosc_handle *h, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -17,32 +17,24 @@ void hm_eig(double d21, double d31, double a, double u1, double u2, double u3, d
     eig_rank_one(d21, d31, a, u1, u2, u3, q, w[0], w[1]);
 }
 
-// P1e[n_paths][n_e] exactly as osc_kernel phases 1a + 2 compute it (one energy chunk, cbs = n_e/2)
+// P1e[n_paths][n_e] with the kernel's own table builder and step functions (one energy chunk)
 void hm_p1e(const double* e_calc, int n_e, const int* path_start, const int* app_layer, const double* app_len,
             int n_paths, const double* lookup, int nl, double s12sq_in, double s13sq_in, double dm21, double* p1e) {
     const int cbs = n_e / 2;
-    std::vector<double> tbl((size_t)11 * nl * n_e);
+    std::vector<double> tbl((size_t)kEntry * nl * n_e);
     const double s12sq = fmin(fmax(s12sq_in, 0.0), 1.0), s13sq = fmin(fmax(s13sq_in, 0.0), 1.0);
     const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq, c13 = sqrt(c13sq);
     const double u1 = sqrt(c12sq) * c13, u2 = sqrt(s12sq) * c13, u3 = sqrt(s13sq);
     for (int k = 0; k < nl; ++k)
         for (int el = 0; el < n_e; ++el) {
-            const double e = e_calc[el];
-            double q[9], w2, w3;
-            eig_rank_one(dm21, kDm31, lookup[k] * e, u1, u2, u3, q, w2, w3);
             const int slot = (el & 1) * cbs + (el >> 1);
-            const double f = kPhase / e;
-            for (int c = 0; c < 9; ++c) tbl[((size_t)c * nl + k) * 2 * cbs + slot] = q[c];
-            tbl[((size_t)9 * nl + k) * 2 * cbs + slot] = f * w2;
-            tbl[((size_t)10 * nl + k) * 2 * cbs + slot] = f * w3;
+            make_entry(dm21, lookup[k] * e_calc[el], e_calc[el], u1, u2, u3, tbl.data() + ((size_t)k * 2 * cbs + slot) * kEntry);
         }
     for (int path = 0; path < n_paths; ++path)
         for (int el = 0; el < n_e; ++el) {
             const int slot = (el & 1) * cbs + (el >> 1);
-            double ar = u1, br = u2, cr = u3, ai = 0, bi = 0, ci = 0;
-            for (int s = path_start[path]; s < path_start[path + 1]; ++s)
-                earth_step(tbl.data() + (size_t)app_layer[s] * 2 * cbs + slot, (size_t)nl * 2 * cbs, app_len[s], ar, ai, br, bi, cr, ci);
-            p1e[(size_t)path * n_e + el] = fma(ar, ar, ai * ai);
+            p1e[(size_t)path * n_e + el] = path_p1e(tbl.data() + (size_t)slot * kEntry, (size_t)2 * cbs * kEntry, app_layer,
+                                                    app_len, path_start[path], path_start[path + 1], u1, u2, u3);
         }
 }
 
