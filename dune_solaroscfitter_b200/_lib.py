@@ -21,7 +21,7 @@ EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
     "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_rates",
     "solarosc_eval_perbin", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
-    "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_measure_fp64_peak",
+    "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
 )
 
 _lib = None
@@ -71,6 +71,7 @@ def load():
     L.solarosc_poisson_llh.argtypes = [H, dp, dp, sz, sz, dp, up]
     L.solarosc_set_timing.argtypes = [H, C.c_int]
     L.solarosc_last_timing.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.solarosc_last_fused.argtypes = [H]
     L.solarosc_measure_fp64_peak.argtypes = [H, dp]
     _lib = L
     return L

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -73,10 +74,15 @@ struct solarosc_handle {
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
     size_t scratch_bytes = 0;
     size_t osc_smem_limit = 200 * 1024;
+    size_t fused_smem = 0, seg_bytes = 0;
+    bool fused_seg = false;
+    bool fused_ok = false;
     std::mutex mu;
     std::string err;
     float ms_osc = 0.f, ms_rates = 0.f;
     int launches = 0;
+    bool use_fused = true;
+    bool last_fused = false;
 
     template <class Tp>
     Tp* dalloc(size_t n) {
@@ -150,6 +156,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
             "fast == 0 needs the solar production-region tables");
     h->cfg = *c;
     h->device = c->device;
+    h->use_fused = std::getenv("SOLAROSC_NO_FUSED") == nullptr;   // A/B switch for profiling
     int n_dev = 0;
     CK(cudaGetDeviceCount(&n_dev));
     if (c->device < 0 || c->device >= n_dev) throw CudaFail{"no such CUDA device"};
@@ -231,15 +238,29 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         h->n_es[d] = D.n_es; h->n_cc[d] = D.n_cc;
         h->max_ereco = std::max({h->max_ereco, D.n_es, D.n_cc});
         const int nT = T.n_etrue;
-        D.u_es_nue_8b = h->upload(s.unosc_es_nue_8b, nT); D.u_es_nuo_8b = h->upload(s.unosc_es_nuother_8b, nT);
-        D.u_cc_8b = h->upload(s.unosc_cc_8b, nT); D.u_es_nue_hep = h->upload(s.unosc_es_nue_hep, nT);
-        D.u_es_nuo_hep = h->upload(s.unosc_es_nuother_hep, nT); D.u_cc_hep = h->upload(s.unosc_cc_hep, nT);
         D.log_e_norm = h->upload(s.log_e_norm, nT);
-        D.r_es_nue = h->upload_vec(to_row_major(s.resp_es_nue, nT, D.n_es, cm, (nT + 1) & ~1));
-        D.r_es_nuo = h->upload_vec(to_row_major(s.resp_es_nuother, nT, D.n_es, cm, (nT + 1) & ~1));
-        D.r_cc = h->upload_vec(to_row_major(s.resp_cc, nT, D.n_cc, cm, (nT + 1) & ~1));
-        D.eff_es_nue = h->upload(s.eff_es_nue, D.n_es); D.eff_es_nuo = h->upload(s.eff_es_nuother, D.n_es);
-        D.eff_cc = h->upload(s.eff_cc, D.n_cc);
+        {   // constant matrices of the fold (derivation at fold_stage in solarosc_kernels.cuh)
+            const std::vector<double> re = to_row_major(s.resp_es_nue, nT, D.n_es, cm), ro = to_row_major(s.resp_es_nuother, nT, D.n_es, cm);
+            const std::vector<double> rc = to_row_major(s.resp_cc, nT, D.n_cc, cm);
+            const int kp = 4 * fold_kt(nT), le = 8 * ((D.n_es + 7) / 8), lc = 8 * ((D.n_cc + 7) / 8);
+            std::vector<double> a8((size_t)kp * le, 0.0), ah(a8), c8(le, 0.0), chh(le, 0.0), b8((size_t)kp * lc, 0.0), bh(b8);
+            for (int i = 0; i < nT; ++i) {
+                for (int j = 0; j < D.n_es; ++j) {
+                    const double xe = s.eff_es_nue[j] * re[(size_t)i * D.n_es + j], xo = s.eff_es_nuother[j] * ro[(size_t)i * D.n_es + j];
+                    a8[(size_t)i * le + j] = 0.5 * (s.unosc_es_nue_8b[i] * xe - s.unosc_es_nuother_8b[i] * xo);
+                    ah[(size_t)i * le + j] = 0.5 * (s.unosc_es_nue_hep[i] * xe - s.unosc_es_nuother_hep[i] * xo);
+                    c8[j] += 0.5 * s.unosc_es_nuother_8b[i] * xo;
+                    chh[j] += 0.5 * s.unosc_es_nuother_hep[i] * xo;
+                }
+                for (int j = 0; j < D.n_cc; ++j) {
+                    const double xc = 0.5 * s.eff_cc[j] * rc[(size_t)i * D.n_cc + j];
+                    b8[(size_t)i * lc + j] = s.unosc_cc_8b[i] * xc;
+                    bh[(size_t)i * lc + j] = s.unosc_cc_hep[i] * xc;
+                }
+            }
+            D.a8 = h->upload_vec(a8); D.ah = h->upload_vec(ah); D.c8 = h->upload_vec(c8); D.ch = h->upload_vec(chh);
+            D.b8 = h->upload_vec(b8); D.bh = h->upload_vec(bh);
+        }
         D.raw_bg_es = h->upload(s.raw_bg_es, (size_t)D.n_bg_es * D.n_es);
         D.raw_bg_cc = h->upload(s.raw_bg_cc, (size_t)D.n_bg_cc * D.n_cc);
         D.n_norm_es = 0; D.n_norm_cc = 0;
@@ -277,11 +298,19 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     h->d_params = h->d_params2[0];
     h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
     const size_t rs = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
-    if (rs > prop.sharedMemPerBlockOptin) throw ArgFail{"binning too large for the rate kernel's shared-memory tile"};
+    if (rs > prop.sharedMemPerBlockOptin) throw ArgFail{"binning too large for the fold's shared-memory tile"};
     CK(cudaFuncSetAttribute(rates_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
+    // the fused kernel needs the whole energy axis of one point in one CTA
+    h->fused_smem = llh_smem_bytes(T.n_layers, T.n_etrue, T.n_cosz, h->max_ereco);
+    h->seg_bytes = sizeof(double) * seg_smem_doubles(T.n_seg, T.n_paths, T.n_cosz);
+    // path tables ride along in shared memory while two CTAs still fit on an SM (or one, if two never did)
+    h->fused_seg = h->fused_smem + h->seg_bytes <= (h->fused_smem * 2 <= 220 * 1024 ? 110 * 1024 : prop.sharedMemPerBlockOptin);
+    if (h->fused_seg) h->fused_smem += h->seg_bytes;
+    h->fused_ok = h->fused_smem <= prop.sharedMemPerBlockOptin;
+    if (h->fused_ok) CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
 }
 
 // ---- launches ------------------------------------------------------------------------------------
@@ -296,28 +325,55 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     int cb = (T.n_etrue + want_chunks - 1) / want_chunks;
     cb = std::max(1, std::min(cb, cb_max));
     const int n_chunks = (T.n_etrue + cb - 1) / cb;
-    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step};
-    osc_kernel<<<n_osc * n_chunks, kOscThreads, osc_smem_bytes(T.n_layers, cb), st>>>(T, L, d_params, h->d_osc, d_p1e);
+    size_t sm = osc_smem_bytes(T.n_layers, cb);
+    const bool seg = sm + h->seg_bytes <= std::min<size_t>(h->osc_smem_limit, 110 * 1024);
+    if (seg) sm += h->seg_bytes;
+    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0};
+    osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, h->d_osc, d_p1e);
     CK(cudaGetLastError());
     ++h->launches;
+}
+
+RatesLaunch rates_launch(solarosc_handle* h, int n, int group, int det_only) {
+    const DevTables& T = h->T;
+    RatesLaunch L{};
+    L.n_points = n; L.group = group; L.param_stride = h->P; L.det_only = det_only; L.max_ereco = h->max_ereco;
+    L.seg_smem = h->fused_seg ? 1 : 0;
+    const int d = det_only >= 0 ? det_only : 0;
+    const bool cm = h->cfg.col_major != 0;
+    L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? T.n_cosz : 1;
+    L.s_row_cc = cm ? 1 : h->n_cc[d]; L.s_j_cc = cm ? T.n_cosz : 1;
+    return L;
 }
 
 void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, int mode, int det_only, RatesOut O,
                   cudaStream_t st) {
     const DevTables& T = h->T;
-    RatesLaunch L{};
-    L.n_points = n; L.group = group; L.param_stride = h->P; L.mode = mode; L.det_only = det_only;
-    const int d = det_only >= 0 ? det_only : 0;
-    const bool cm = h->cfg.col_major != 0;
-    L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? T.n_cosz : 1;
-    L.s_row_cc = cm ? 1 : h->n_cc[d]; L.s_j_cc = cm ? T.n_cosz : 1;
-    L.max_ereco = h->max_ereco;
+    const RatesLaunch L = rates_launch(h, n, group, det_only);
     const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
-    if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
-    else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
-    else rates_kernel<kModePerbin><<<n, kRatesThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    else rates_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     CK(cudaGetLastError());
     ++h->launches;
+}
+
+// lnL of n points; the fused kernel when the batch fills the GPU, otherwise the energy-split
+// oscillation kernel followed by the fold kernel.  Returns true when the fused kernel ran.
+bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid) {
+    const int n_osc = n / group;
+    if (h->fused_ok && h->use_fused && n_osc >= h->sm_count) {
+        const RatesLaunch L = rates_launch(h, n, group, -1);
+        llh_kernel<kModeLlh><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        CK(cudaGetLastError());
+        ++h->launches;
+        if (mid) CK(cudaEventRecord(mid, st));
+        return true;
+    }
+    launch_osc(h, d_params, n_osc, group, nullptr, st);
+    if (mid) CK(cudaEventRecord(mid, st));
+    launch_rates(h, d_params, n, group, kModeLlh, -1, O, st);
+    return false;
 }
 
 void check_data(solarosc_handle* h, int det_only) {
@@ -376,12 +432,11 @@ int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t gro
         CK(cudaEventRecord(h->ev_in[slot], h->s_in));
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));  // results of chunk c-2 have left this slot
-        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
-        launch_osc(h, h->d_params2[slot], nb / (int)group, (int)group, nullptr, h->stream);
-        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
         RatesOut O{};
         O.lnl = h->d_lnl2[slot]; O.flags = h->d_flags2[slot];
-        launch_rates(h, h->d_params2[slot], nb, (int)group, kModeLlh, -1, O, h->stream);
+        if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
+        cudaEvent_t mid = h->timing ? h->next_tev() : nullptr;
+        h->last_fused = launch_llh(h, h->d_params2[slot], nb, (int)group, O, h->stream, mid);
         if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
         CK(cudaEventRecord(h->ev_done[slot], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
@@ -603,13 +658,12 @@ int solarosc_eval_llh_device(solarosc_handle* h, const double* d_params, size_t 
         h->tev_stream = st;
         for (size_t b0 = 0; b0 < n; b0 += step) {
             const int nb = (int)std::min(step, n - b0);
-            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
-            launch_osc(h, d_params + b0 * h->P, nb / (int)group, (int)group, nullptr, st);
-            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
             RatesOut O{};
             O.lnl = d_lnl + b0;
             O.flags = d_flags ? d_flags + b0 : nullptr;
-            launch_rates(h, d_params + b0 * h->P, nb, (int)group, kModeLlh, -1, O, st);
+            if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
+            cudaEvent_t mid = h->timing ? h->next_tev() : nullptr;
+            h->last_fused = launch_llh(h, d_params + b0 * h->P, nb, (int)group, O, st, mid);
             if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
         }
         return (int)SOLAROSC_OK;
@@ -670,6 +724,8 @@ int solarosc_last_timing(solarosc_handle* h, float* ms_osc, float* ms_rates) {
     if (ms_rates) *ms_rates = c;
     return h->launches;
 }
+
+int solarosc_last_fused(const solarosc_handle* h) { return h ? (h->last_fused ? 1 : 0) : -1; }
 
 int solarosc_measure_fp64_peak(solarosc_handle* h, double* tflops) {
     return guarded(h, [&]() {

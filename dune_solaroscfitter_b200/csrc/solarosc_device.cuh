@@ -21,10 +21,11 @@ constexpr int kMaxDet = 4;
 
 struct DevDetector {
     int es_mode, cc_mode, n_es, n_cc, index_es, index_cc, n_bg_es, n_bg_cc, n_norm_es, n_norm_cc, param_off;
-    // all [n_etrue]
-    const double *u_es_nue_8b, *u_es_nuo_8b, *u_cc_8b, *u_es_nue_hep, *u_es_nuo_hep, *u_cc_hep, *log_e_norm;
-    // responses stored [n_etrue][n_ereco] (j fastest), efficiencies [n_ereco]
-    const double *r_es_nue, *r_es_nuo, *r_cc, *eff_es_nue, *eff_es_nuo, *eff_cc;
+    const double* log_e_norm;             // [n_etrue]
+    // fold matrices built at create (see fold_stage): [4*ceil(n_etrue/4)][8*ceil(n_ereco/8)], zero padded
+    const double *a8, *ah;                // ES, 8B / hep
+    const double *b8, *bh;                // CC, 8B / hep (without the per-point cross-section shape)
+    const double *c8, *ch;                // ES additive constants per reco bin, [8*ceil(n_es/8)]
     const double *raw_bg_es, *raw_bg_cc;  // [n_bg][n_ereco]
     double bg_es_area[SOLAROSC_MAX_BG];   // face area per ES component (0 => not scaled by a nuisance)
     int bg_cc_norm[SOLAROSC_MAX_BG];      // index of the CC nuisance scaling component i, -1 => fixed

@@ -1,12 +1,18 @@
-// solarosc_kernels.cuh -- the two batched kernels of the hot path.
+// solarosc_kernels.cuh -- the batched kernels of the hot path.
 //
-//   osc_kernel    K1 + K2: adiabatic MSW day probability (mean density or production-region
-//                 integral) and Earth-matter P1e through the layered path table, fused with the
-//                 IYSW night formula and the (N_COSZ_SUB x 2) block average.  One CTA per
-//                 (parameter point, chunk of coarse energy bins).
-//   rates_kernel  K3 + K4 + K5: flux x cross-section x exposure weighting, E_true -> E_reco fold
-//                 for ES nu_e / ES nu_other / CC, background addition and the soft-floored Poisson
-//                 log-likelihood reduced with warp shuffles.  One CTA per parameter point.
+//   osc_stage   K1 + K2: adiabatic MSW day probability (mean density or production-region integral)
+//               and Earth-matter P1e through the layered path table, fused with the IYSW night
+//               formula and the (N_COSZ_SUB x 2) block average.
+//   fold_stage  K3 + K4 + K5: flux x cross-section x exposure weighting, E_true -> E_reco fold for
+//               ES nu_e / ES nu_other / CC on the FP64 tensor pipe (DMMA m8n8k4), background
+//               addition and the soft-floored Poisson log-likelihood reduced with warp shuffles.
+//
+//   llh_kernel    one CTA per oscillation point: osc_stage into shared memory, then fold_stage for
+//                 every parameter point that shares it (1 in general, n_sys x 3 for an LLH-scan cell).
+//                 The oscillation probabilities never leave the SM.
+//   osc_kernel    osc_stage alone, energy axis optionally split over CTAs, probabilities to HBM
+//                 (stage-separated API, small batches).
+//   rates_kernel  fold_stage alone on probabilities read back from HBM.
 //
 // Reference code each stage stands in for is cited at the stage.
 #pragma once
@@ -20,9 +26,9 @@ namespace solarosc {
 #ifndef SOLAROSC_OSC_MINBLOCKS
 #define SOLAROSC_OSC_MINBLOCKS 2
 #endif
-constexpr int kOscThreads = SOLAROSC_OSC_THREADS;
-constexpr int kRatesThreads = 256;
-constexpr int kRT = 7;   // rows of the fold kept in registers per thread
+constexpr int kThreads = SOLAROSC_OSC_THREADS;   // every kernel here uses this block size
+constexpr int kWarps = kThreads / 32;
+constexpr int kMC = 4;   // row tiles of the fold a warp keeps in flight
 
 struct OscLaunch {
     int n_points;     // oscillation points in this launch
@@ -30,31 +36,116 @@ struct OscLaunch {
     int cb;           // coarse energy bins per chunk
     int param_stride; // doubles between consecutive points' parameter rows
     int point_step;   // parameter row of oscillation point g is g*point_step (grouped evaluation)
+    int seg_smem;     // path tables staged in shared memory behind the eigen table
 };
 
-__host__ __device__ inline size_t osc_smem_bytes(int n_layers, int cb) {
-    return sizeof(double) * ((size_t)kEntry * n_layers * 2 * cb + (size_t)4 * 2 * cb);
+enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2 };
+
+struct RatesLaunch {
+    int n_points;
+    int group;         // points per shared oscillation stage
+    int param_stride;
+    int det_only;      // -1: all detectors (likelihood), else the one detector whose arrays are written
+    int max_ereco;     // largest reco-bin count of any detector/channel (sizes the shared-memory tiles)
+    int seg_smem;      // fused kernel: path tables staged in shared memory behind the scratch
+    long long s_row_es, s_j_es, s_row_cc, s_j_cc;  // output strides of the night arrays (layout)
+};
+
+struct RatesOut {
+    double* lnl; uint32_t* flags;
+    double *es_day, *es_night, *cc_day, *cc_night, *bg_es, *bg_cc;
+};
+
+// ---- shared-memory geometry ------------------------------------------------------------------------
+__host__ __device__ inline size_t osc_smem_doubles(int n_layers, int cb) {
+    return (size_t)kEntry * n_layers * 2 * cb + (size_t)4 * 2 * cb;
+}
+__host__ __device__ inline size_t osc_smem_bytes(int n_layers, int cb) { return sizeof(double) * osc_smem_doubles(n_layers, cb); }
+
+// Oscillation probabilities as the A operand of the fold: [proc][rows padded to 8][ldp] doubles.  ldp is
+// the K extent rounded up to 4, plus padding to 12 (mod 16): the 8 rows x 4 energies a DMMA A-fragment
+// load touches then fall into distinct bank octets.
+__host__ __device__ inline int fold_kt(int n_etrue) { return (n_etrue + 3) / 4; }
+__host__ __device__ inline int fold_ldp(int n_etrue) {
+    int l = 4 * fold_kt(n_etrue);
+    while (l % 16 != 12) l += 4;
+    return l;
+}
+__host__ __device__ inline int fold_rows(int nrow) { return 8 * ((nrow + 7) / 8); }
+__host__ __device__ inline size_t fold_p_doubles(int n_etrue, int nrow) { return (size_t)2 * fold_rows(nrow) * fold_ldp(n_etrue); }
+__host__ __device__ inline size_t fold_scratch_doubles(int n_etrue, int max_ereco) {
+    return (size_t)4 * fold_kt(n_etrue) + (size_t)2 * 8 * ((max_ereco + 7) / 8) + 8;
+}
+// folded rates of both channels, [2][rows padded to 8][reco bins padded to 8]
+__host__ __device__ inline size_t fold_r_doubles(int nrow, int max_ereco) {
+    return (size_t)2 * fold_rows(nrow) * 8 * ((max_ereco + 7) / 8);
+}
+__host__ __device__ inline size_t rates_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
+    return sizeof(double) * (fold_r_doubles(1 + n_cosz, max_ereco) + fold_p_doubles(n_etrue, 1 + n_cosz) +
+                             fold_scratch_doubles(n_etrue, max_ereco));
+}
+// in the fused kernel the folded-rate tiles reuse the eigen table's space, which is dead by then
+__host__ __device__ inline size_t llh_front_doubles(int n_layers, int n_etrue, int n_cosz, int max_ereco) {
+    const size_t a = osc_smem_doubles(n_layers, n_etrue), r = fold_r_doubles(1 + n_cosz, max_ereco);
+    return a > r ? a : r;
+}
+__host__ __device__ inline size_t llh_smem_bytes(int n_layers, int n_etrue, int n_cosz, int max_ereco) {
+    return sizeof(double) * (llh_front_doubles(n_layers, n_etrue, n_cosz, max_ereco) + fold_p_doubles(n_etrue, 1 + n_cosz) +
+                             fold_scratch_doubles(n_etrue, max_ereco));
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 + K2
+// K1 + K2.  `sink.put(row, i, p8, ph)` receives the block-averaged nu_e survival probabilities of
+// coarse energy bin i for row 0 (day) and rows 1 + z (night zenith bin z).  Ends without a barrier.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kOscThreads, SOLAROSC_OSC_MINBLOCKS)
-osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ params,
-           double* __restrict__ osc_out /* [n_points][2][1+n_cosz][n_etrue] */,
-           double* __restrict__ p1e_out /* [n_points][n_paths][n_e] or nullptr */) {
-    extern __shared__ double smem[];
-    const int g = blockIdx.x / L.n_chunks;
-    const int chunk = blockIdx.x - g * L.n_chunks;
-    const int i0 = chunk * L.cb;                         // first coarse energy bin of this CTA
-    const int cb = min(L.cb, T.n_etrue - i0);            // coarse bins handled here
-    const int ne = 2 * cb;                               // fine energies handled here
-    const int nl = T.n_layers;
-    const int cbs = L.cb;                                // table stride (full chunk size)
-    double* tbl = smem;                                  // [nl][2 parity][cbs] entries of kEntry doubles
-    double* msw = smem + (size_t)kEntry * nl * 2 * cbs;  // [2 proc][2 what][2 parity][cbs]
-    const double* p = params + (size_t)g * L.point_step * L.param_stride;
+struct GlobalSink {
+    double *out8, *outh;
+    int n_etrue;
+    __device__ __forceinline__ void put(int row, int i, double p8, double ph) const {
+        out8[(size_t)row * n_etrue + i] = p8;
+        outh[(size_t)row * n_etrue + i] = ph;
+    }
+};
+struct SmemSink {
+    double *p8s, *phs;
+    int ldp;
+    __device__ __forceinline__ void put(int row, int i, double p8, double ph) const {
+        p8s[row * ldp + i] = p8;
+        phs[row * ldp + i] = ph;
+    }
+};
 
+// Path tables as the propagation loop reads them: in shared memory when they fit (every layer step
+// needs its layer id and length, and a global load there sits on the critical path), else in HBM.
+struct SegTables {
+    const int* path_start;
+    const int* app_layer;
+    const double* app_len;
+    const int* row_order;
+};
+
+__host__ __device__ inline size_t seg_smem_doubles(int n_seg, int n_paths, int n_cosz) {
+    return (size_t)n_seg + ((size_t)n_seg + n_paths + 1 + n_cosz + 1) / 2 + 1;
+}
+
+// Copies the path tables behind `buf` (no barrier: the caller's next __syncthreads orders it).
+__device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double* buf, bool to_smem) {
+    if (!to_smem) return SegTables{T.path_start, T.app_layer, T.app_len, T.row_order};
+    double* len = buf;
+    int* lay = reinterpret_cast<int*>(buf + T.n_seg);
+    int* start = lay + T.n_seg;
+    int* order = start + T.n_paths + 1;
+    for (int t = threadIdx.x; t < T.n_seg; t += blockDim.x) { len[t] = T.app_len[t]; lay[t] = T.app_layer[t]; }
+    for (int t = threadIdx.x; t <= T.n_paths; t += blockDim.x) start[t] = T.path_start[t];
+    for (int t = threadIdx.x; t < T.n_cosz; t += blockDim.x) order[t] = T.row_order[t];
+    return SegTables{start, lay, len, order};
+}
+
+template <class Sink>
+__device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G, const double* __restrict__ p, int i0, int cb,
+                                          int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink) {
+    const int ne = 2 * cb;   // fine energies handled here
+    const int nl = T.n_layers;
     // mixing parameters (reference propagation_osc.jl:30-36: theta = asin(sqrt(clamp(sin2, 0, 1))))
     const double s12sq = fmin(fmax(p[0], 0.0), 1.0), s13sq = fmin(fmax(p[1], 0.0), 1.0);
     const double dm21 = p[2];
@@ -103,15 +194,10 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     }
     __syncthreads();
 
-    const int nrow = 1 + T.n_cosz;
-    double* out8 = osc_out + (size_t)g * 2 * nrow * T.n_etrue;
-    double* outh = out8 + (size_t)nrow * T.n_etrue;
-
     // ---- day rows: block_average(prob_day, 2)  (propagation_osc.jl:133-134) -----------------------
-    for (int j = threadIdx.x; j < cb; j += blockDim.x) {
-        out8[i0 + j] = 0.5 * (msw[j] + msw[cbs + j]);
-        outh[i0 + j] = 0.5 * (msw[(size_t)2 * 2 * cbs + j] + msw[(size_t)2 * 2 * cbs + cbs + j]);
-    }
+    for (int j = threadIdx.x; j < cb; j += blockDim.x)
+        sink.put(0, i0 + j, 0.5 * (msw[j] + msw[cbs + j]),
+                 0.5 * (msw[(size_t)2 * 2 * cbs + j] + msw[(size_t)2 * 2 * cbs + cbs + j]));
 
     // ---- phase 2: Earth propagation, one item = (coarse zenith row, coarse energy bin) -----------
     // Lanes of a warp walk the same path at neighbouring energies, so the layer loop is
@@ -120,20 +206,20 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     const int n_items = T.n_cosz * cb;
     for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
         const int zr = item / cb, j = item - zr * cb;
-        const int z = T.row_order[zr];
+        const int z = G.row_order[zr];
         double acc8 = 0.0, acch = 0.0;
         const double* t0 = tbl + (size_t)j * kEntry;           // even fine energy of this coarse bin, layer 0
         const double* t1 = t0 + (size_t)cbs * kEntry;          // odd fine energy
         const int ls = 2 * cbs * kEntry;                        // doubles between consecutive layers
         for (int sub = 0; sub < T.n_sub; ++sub) {
             const int path = z * T.n_sub + sub;
-            const int s0 = T.path_start[path], s1 = T.path_start[path + 1];
+            const int s0 = G.path_start[path], s1 = G.path_start[path + 1];
             // Both fine energies of the bin advance through the layers together: two independent
             // dependency chains per thread keep the FP64 pipe fed (osc_reduce_from_lookup, osc.jl:436-446).
             State pa, pb;
             {
-                const int k = T.app_layer[s0] * ls;
-                const double len = T.app_len[s0];
+                const int k = G.app_layer[s0] * ls;
+                const double len = G.app_len[s0];
                 if (s1 - s0 == 1) {
                     double y1r, y1i, y2r, y2i;
                     step_phases(t0 + k, len, y1r, y1i, y2r, y2i);
@@ -146,13 +232,13 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
                     step_first(t0 + k, len, u1, u2, u3, pa);
                     step_first(t1 + k, len, u1, u2, u3, pb);
                     for (int s = s0 + 1; s < s1 - 1; ++s) {
-                        const int km = T.app_layer[s] * ls;
-                        const double lm = T.app_len[s];
+                        const int km = G.app_layer[s] * ls;
+                        const double lm = G.app_len[s];
                         step_mid(t0 + km, lm, pa);
                         step_mid(t1 + km, lm, pb);
                     }
-                    const int kl = T.app_layer[s1 - 1] * ls;
-                    const double ll = T.app_len[s1 - 1];
+                    const int kl = G.app_layer[s1 - 1] * ls;
+                    const double ll = G.app_len[s1 - 1];
                     step_last(t0 + kl, ll, pa);
                     step_last(t1 + kl, ll, pb);
                 }
@@ -160,7 +246,7 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
             const double pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);   // |<nu_1|X|nu_e>|^2 (osc.jl:444)
             const double pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
             if (p1e_out) {
-                double* o = p1e_out + ((size_t)g * T.n_paths + path) * T.n_e + 2 * (i0 + j);
+                double* o = p1e_out + (size_t)path * T.n_e + 2 * (i0 + j);
                 o[0] = pe0; o[1] = pe1;
             }
             // IYSW night probability (osc.jl:204): P_day + c13^2 cos2theta_m (P1e - P0)
@@ -169,52 +255,66 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
             acch += fma(msw[(size_t)3 * 2 * cbs + j], d0, msw[(size_t)2 * 2 * cbs + j]) +
                     fma(msw[(size_t)3 * 2 * cbs + cbs + j], d1, msw[(size_t)2 * 2 * cbs + cbs + j]);
         }
-        out8[(size_t)(1 + z) * T.n_etrue + i0 + j] = acc8 * inv_block;   // block_average (propagation_osc.jl:136-137)
-        outh[(size_t)(1 + z) * T.n_etrue + i0 + j] = acch * inv_block;
+        sink.put(1 + z, i0 + j, acc8 * inv_block, acch * inv_block);   // block_average (propagation_osc.jl:136-137)
     }
+}
+
+__global__ void __launch_bounds__(kThreads, SOLAROSC_OSC_MINBLOCKS)
+osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ params,
+           double* __restrict__ osc_out /* [n_points][2][1+n_cosz][n_etrue] */,
+           double* __restrict__ p1e_out /* [n_points][n_paths][n_e] or nullptr */) {
+    extern __shared__ double smem[];
+    const int g = blockIdx.x / L.n_chunks;
+    const int chunk = blockIdx.x - g * L.n_chunks;
+    const int i0 = chunk * L.cb;                         // first coarse energy bin of this CTA
+    const int cb = min(L.cb, T.n_etrue - i0);            // coarse bins handled here
+    const int nrow = 1 + T.n_cosz;
+    double* tbl = smem;                                  // [nl][2 parity][cbs] entries of kEntry doubles
+    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * L.cb;   // [2 proc][2 what][2 parity][cbs]
+    const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_layers, L.cb), L.seg_smem != 0);
+    GlobalSink sink{osc_out + (size_t)g * 2 * nrow * T.n_etrue, osc_out + ((size_t)g * 2 + 1) * nrow * T.n_etrue, T.n_etrue};
+    osc_stage(T, G, params + (size_t)g * L.point_step * L.param_stride, i0, cb, L.cb, tbl, msw,
+              p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr, sink);
 }
 
 // ------------------------------------------------------------------------------------------
 // K3 + K4 + K5
 // ------------------------------------------------------------------------------------------
-enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2 };
-
-struct RatesLaunch {
-    int n_points;
-    int group;         // points per shared oscillation stage
-    int param_stride;
-    int mode;          // RatesMode
-    int det_only;      // -1: all detectors (likelihood), else the one detector whose arrays are written
-    int max_ereco;     // largest reco-bin count of any detector/channel (sizes the shared-memory tiles)
-    long long s_row_es, s_j_es, s_row_cc, s_j_cc;  // output strides of the night arrays (layout)
-};
-
-struct RatesOut {
-    double* lnl; uint32_t* flags;
-    double *es_day, *es_night, *cc_day, *cc_night, *bg_es, *bg_cc;
-};
-
-// rows of the oscillated sample are padded to a multiple of the per-pass row count and then to
-// pitch = 1 (mod 8) so that the transposing stores of consecutive energies hit distinct banks
-__host__ __device__ inline int rates_row_pitch(int nrow) {
-    const int per_pass = (kRatesThreads / 32) * kRT;
-    int p = ((nrow + per_pass - 1) / per_pass) * per_pass;
-    while (p % 8 != 1) ++p;
-    return p;
+// Natural logarithm of a positive, finite, normal double (every soft-floored expectation is one): the
+// fdlibm algorithm -- x = 2^k m, m in [sqrt(1/2), sqrt(2)), log m = 2s + s R(s^2), s = (m-1)/(m+1) -- with
+// the division done as reciprocal seed + Newton steps.  Error below 1 ulp, about a third of the
+// instructions of the general-purpose log() with its special-case handling.
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi > 0x3ff6a09e) { hi -= 0x00100000; k += 1; }
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double t = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    r = fma(fma(-t, r, 1.0), r, r);
+    r = fma(fma(-t, r, 1.0), r, r);
+    double sq = f * r;
+    sq = fma(fma(-t, sq, f), r, sq);                       // s = f / (2 + f), correctly rounded to ~1 ulp
+    const double z = sq * sq, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)k;
+    return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
 }
 
-__host__ __device__ inline size_t rates_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
-    const size_t ld = (size_t)((n_etrue + 1) & ~1);
-    return sizeof(double) * ((size_t)3 * rates_row_pitch(1 + n_cosz) * ld + 2 * ld + (size_t)2 * max_ereco +
-                             (size_t)2 * (1 + n_cosz) * max_ereco + 16);
-}
-
-// soft-floored Poisson term (reference likelihood_statistical.jl:16-24)
+// soft-floored Poisson term (reference likelihood_statistical.jl:16-24).  For raw_e - 1e-9 > 0.1 the
+// square root returns its argument's root exactly (the 1e-18 is below half an ulp of d^2), so the fast
+// branch is bit-identical to the formula.
 __device__ __forceinline__ double poisson_term(double raw_e, double m, double logm, uint32_t& fl) {
     if (raw_e < 0.0) fl |= (raw_e > -1e-3) ? SOLAROSC_FLAG_NEG_WARN : SOLAROSC_FLAG_NEG_ERROR;
     const double d = raw_e - 1e-9;
-    const double e = 0.5 * (raw_e + 1e-9 + sqrt(fma(d, d, 1e-18)));
-    return (m > 0.0) ? (e - m + m * (logm - log(e))) : e;
+    const double root = (d > 0.1) ? d : sqrt(fma(d, d, 1e-18));
+    const double e = 0.5 * (raw_e + 1e-9 + root);
+    return (m > 0.0) ? (e - m + m * (logm - log_pos(e))) : e;
 }
 
 // per-bin diagnostic term (reference likelihood_statistical.jl:31-57)
@@ -227,31 +327,35 @@ __device__ __forceinline__ double perbin_term(double raw_e, double m) {
     return -raw_e;
 }
 
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe.  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
+// D[l>>2][2*(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// The response fold is linear in the oscillation probabilities, so everything that does not depend on
+// the parameter point is folded into constant matrices at create time (host: build_fold_tables):
+//   ES[row][j] = w_row * ( F8 * sum_i P8[row][i] A8[i][j] + Fh * sum_i Ph[row][i] Ah[i][j] + cst_es[j] )
+//   CC[row][j] = w_row * ( F8 * sum_i P8[row][i] s_i B8[i][j] + Fh * sum_i Ph[row][i] s_i Bh[i][j] + cst_cc[j] )
+// with A = 0.5 (eff_nue u_nue R_nue - eff_nuo u_nuo R_nuo), B = 0.5 eff_cc u_cc R_cc, s_i the CC
+// cross-section shape, w_0 = 1 (day) and w_{1+z} the exposure weight, cst_es = F8 C8 + Fh Ch + BG_ES/2,
+// cst_cc = BG_CC/2 (reference propagation_osc.jl:159-210, propagation_core.jl:73-79,
+// propagation_reco.jl:10-29,117-130 rearranged; same arithmetic up to rounding order).
+// One warp owns one (channel, 8 reco bins) column block and sweeps the row tiles: per k-step it
+// loads two A fragments from shared memory, two B fragments through L1 and issues two DMMAs, so the
+// FP64 pipe, not the issue slots or the shared-memory port, limits the fold.
 template <int MODE>
-__global__ void __launch_bounds__(kRatesThreads)
-rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params,
-             const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
-    extern __shared__ double smem[];
-    const int b = blockIdx.x;
+__device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
+                                           const double* p8s, const double* phs, int ldp, double* scr, double* rbuf,
+                                           const RatesOut& O, double* red, uint32_t* redf) {
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
-    const int ldS = (nT + 1) & ~1;           // true energies padded to an even count
-    const int npair = ldS >> 1;
-    const int nrp = rates_row_pitch(nrow);   // padded row count of the pair-major oscillated sample
-    double* S0 = smem;                       // oscillated sample, ES nu_e      [npair][nrp] double2
-    double* S1 = S0 + (size_t)nrp * ldS;     //                    ES nu_other
-    double* S2 = S1 + (size_t)nrp * ldS;     //                    CC
-    double* ccs = S2 + (size_t)nrp * ldS;    // CC unoscillated sample x cross-section shape, 8B then hep
-    double* bgs = ccs + 2 * (size_t)ldS;     // summed backgrounds, ES then CC
-    double* rates_es = bgs + 2 * (size_t)L.max_ereco;            // folded rates [nrow][n_ereco]
-    double* rates_cc = rates_es + (size_t)nrow * L.max_ereco;
-    __shared__ double red[kRatesThreads / 32];
-    __shared__ uint32_t redf[kRatesThreads / 32];
-
-    const double* p = params + (size_t)b * L.param_stride;
-    const double* P8 = osc + (size_t)(b / L.group) * 2 * nrow * nT;
-    const double* Ph = P8 + (size_t)nrow * nT;
+    const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fg = lane >> 2, ft = lane & 3;
     const double f8 = p[3], fh = p[4];
-
+    double* shape = scr;                     // [4*kt] CC cross-section shape, zero padded
+    double* cst_es = scr + 4 * kt;           // per reco bin additive constants
     // earth-norm bounds (reference likelihood_debug.jl:1-4, likelihood_builder.jl:227)
     bool oob = false;
     if (T.earth_unc)
@@ -259,179 +363,152 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
             const double x = p[SOLAROSC_N_FIXED_PARAMS + k];
             oob |= !(x >= 0.0 && x <= 2.0);
         }
-
     double total = 0.0;
     uint32_t fl = 0;
     for (int di = 0; di < T.n_det; ++di) {
         if (L.det_only >= 0 && di != L.det_only) continue;
         const DevDetector& D = T.det[di];
         const double* pd = p + D.param_off;
-        double* bg_es = bgs;
-        double* bg_cc = bgs + D.n_es;
-        __syncthreads();
-        // ---- backgrounds (reference propagation_bg.jl:36-83; every ES component uses norm_1) ----
-        for (int j = threadIdx.x; j < D.n_es + D.n_cc; j += blockDim.x) {
-            double acc = 0.0;
-            if (j < D.n_es) {
-                for (int c = 0; c < D.n_bg_es; ++c) {
-                    const double raw = D.raw_bg_es[(size_t)c * D.n_es + j];
-                    acc += (D.bg_es_area[c] != 0.0) ? raw * (D.bg_es_area[c] * pd[0]) : raw;
+        const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
+        double* cst_cc = cst_es + 8 * nte;
+        __syncthreads();   // the previous point / detector is done with the scratch
+        // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
+        //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
+        for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
+            double s = 0.0;
+            if (i < nT) {
+                const double l = D.log_e_norm[i];
+                s = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
+            }
+            shape[i] = s;
+        }
+        for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
+            double acc = 0.0, c = 0.0;
+            if (j < 8 * nte) {
+                if (j < D.n_es) {
+                    for (int q = 0; q < D.n_bg_es; ++q) {
+                        const double raw = D.raw_bg_es[q * D.n_es + j];
+                        acc += (D.bg_es_area[q] != 0.0) ? raw * (D.bg_es_area[q] * pd[0]) : raw;
+                    }
+                    c = fma(f8, D.c8[j], fma(fh, D.ch[j], 0.5 * acc));
+                    if (MODE == kModeRates && O.bg_es) O.bg_es[b * D.n_es + j] = acc;
                 }
-                bg_es[j] = acc;
-                if (MODE == kModeRates && O.bg_es) O.bg_es[(size_t)b * D.n_es + j] = acc;
+                cst_es[j] = c;
             } else {
-                const int jc = j - D.n_es;
-                for (int c = 0; c < D.n_bg_cc; ++c) {
-                    const double raw = D.raw_bg_cc[(size_t)c * D.n_cc + jc];
-                    acc += (D.bg_cc_norm[c] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[c]] / 2.2e-6) : raw;
-                }
-                bg_cc[jc] = acc;
-                if (MODE == kModeRates && O.bg_cc) O.bg_cc[(size_t)b * D.n_cc + jc] = acc;
-            }
-        }
-        // ---- CC cross-section shape, once per true-energy bin (reference propagation_osc.jl:185-196) ----
-        for (int i = threadIdx.x; i < nT; i += blockDim.x) {
-            const double l = D.log_e_norm[i];
-            const double shape = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
-            ccs[i] = D.u_cc_8b[i] * shape;
-            ccs[nT + i] = D.u_cc_hep[i] * shape;
-        }
-        __syncthreads();
-        // ---- oscillated samples (reference propagation_osc.jl:159-210) ----------------------------
-        // Stored pair-major, S[(i/2)][row] as double2 = (S[row][i], S[row][i+1]): the fold below reads
-        // the rows r, r+8, r+16, ... of one energy pair at constant offsets from a single pointer.
-        // (row, i) walk all nrow x nT elements with a stride of blockDim.x, updated incrementally so the
-        // loop carries no integer division.
-        if (nT & 1)   // odd number of true-energy bins: the pad element of the last pair must read as 0
-            for (int row = threadIdx.x; row < nrow; row += blockDim.x) {
-                const int dst = 2 * ((npair - 1) * nrp + row) + 1;
-                S0[dst] = 0.0; S1[dst] = 0.0; S2[dst] = 0.0;
-            }
-        {
-            const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
-            int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;
-            while (row < nrow) {
-                const int dst = 2 * ((i >> 1) * nrp + row) + (i & 1);
-                const double p8 = P8[row * nT + i], ph = Ph[row * nT + i];
-                const double w = (row == 0) ? 1.0 : T.wz[row - 1];
-                if (D.es_mode) {
-                    if (row == 0) {
-                        S0[dst] = D.u_es_nue_8b[i] * p8 * f8 + D.u_es_nue_hep[i] * ph * fh;
-                        S1[dst] = D.u_es_nuo_8b[i] * (1.0 - p8) * f8 + D.u_es_nuo_hep[i] * (1.0 - ph) * fh;
-                    } else {
-                        S0[dst] = D.u_es_nue_8b[i] * (f8 * p8 * w) + D.u_es_nue_hep[i] * (fh * ph * w);
-                        S1[dst] = D.u_es_nuo_8b[i] * (f8 * (1.0 - p8) * w) + D.u_es_nuo_hep[i] * (fh * (1.0 - ph) * w);
+                const int jc = j - 8 * nte;
+                if (jc < D.n_cc) {
+                    for (int q = 0; q < D.n_bg_cc; ++q) {
+                        const double raw = D.raw_bg_cc[q * D.n_cc + jc];
+                        acc += (D.bg_cc_norm[q] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[q]] / 2.2e-6) : raw;
                     }
+                    c = 0.5 * acc;
+                    if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
                 }
-                if (D.cc_mode) {
-                    const double c8 = ccs[i], ch = ccs[nT + i];
-                    S2[dst] = (row == 0) ? c8 * p8 * f8 + ch * ph * fh : c8 * (f8 * p8 * w) + ch * (fh * ph * w);
-                }
-                i += dr; row += dq;
-                if (i >= nT) { i -= nT; ++row; }
+                cst_cc[jc] = c;
             }
         }
         __syncthreads();
-        // ---- fold + background + Poisson (reference propagation_core.jl:73-79,
-        //      propagation_reco.jl:10-29,117-130, likelihood_builder.jl:5-20,129-144) ------------------
-        // Lane = reconstructed-energy bin j, warp w owns rows w, w+8, ...: each response element
-        // R[i][j] is loaded once per thread and reused for kRT rows; the oscillated sample comes
-        // from shared memory as warp-wide broadcasts of (i, i+1) pairs.
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        constexpr int kW = kRatesThreads / 32;
-        for (int ch = 0; ch < 2; ++ch) {
-            const bool is_es = ch == 0;
+        // ---- fold on the FP64 tensor pipe: one (channel, 8-bin column block) per warp pass; kMC row tiles
+        //      stay in flight, so every k-step issues 2*kMC independent DMMAs behind two B-fragment loads -----
+        const int ldr = 8 * max(nte, ntc);                  // row pitch of the folded-rate tiles
+        double* rates_es = rbuf;
+        double* rates_cc = rbuf + (size_t)8 * mt * ldr;
+        for (int task = warp; task < nte + ntc; task += kWarps) {
+            const bool is_es = task < nte;
             if (is_es ? !D.es_mode : !D.cc_mode) continue;
-            const int nR = is_es ? D.n_es : D.n_cc;
-            const double* bgv = is_es ? bg_es : bg_cc;
-            double* rout = is_es ? rates_es : rates_cc;
-            for (int j0 = 0; j0 < nR; j0 += 32) {
-                const int j = min(j0 + lane, nR - 1);
-                const bool jv = j0 + lane < nR;
-                const double effa = is_es ? D.eff_es_nue[j] : D.eff_cc[j];
-                const double effb = is_es ? D.eff_es_nuo[j] : 0.0;
-                const double bgj = bgv[j];
-                for (int r0 = warp; r0 < nrow; r0 += kW * kRT) {
-                    double acca[kRT], accb[kRT];
+            const int n0 = 8 * (is_es ? task : task - nte);
+            const int ldb = 8 * (is_es ? nte : ntc);
+            const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
+            const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
+            const int j0 = n0 + 2 * ft;                                      // this lane's two columns
+            const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
+            double* rout = (is_es ? rates_es : rates_cc) + j0;
+            for (int m0 = 0; m0 < mt; m0 += kMC) {
+                double d8[kMC][2], dh[kMC][2];
 #pragma unroll
-                    for (int k = 0; k < kRT; ++k) { acca[k] = 0.0; accb[k] = 0.0; }
-                    if (is_es) {
-                        const double2* sa = reinterpret_cast<const double2*>(S0) + r0;
-                        const double2* sb = reinterpret_cast<const double2*>(S1) + r0;
-                        const double* ra = D.r_es_nue + j;
-                        const double* rb = D.r_es_nuo + j;
-                        for (int i2 = 0; i2 < npair; ++i2) {
-                            const double ra0 = __ldg(ra), ra1 = __ldg(ra + nR);
-                            const double rb0 = __ldg(rb), rb1 = __ldg(rb + nR);
+                for (int c = 0; c < kMC; ++c) { d8[c][0] = d8[c][1] = dh[c][0] = dh[c][1] = 0.0; }
+                const double* a8p = p8s + (8 * m0 + fg) * ldp + ft;
+                const double* ahp = phs + (8 * m0 + fg) * ldp + ft;
+                for (int ks = 0; ks < kt; ++ks) {
+                    const double b8v = __ldg(m8 + 4 * ks * ldb), bhv = __ldg(mh + 4 * ks * ldb);
+                    const double s = is_es ? 1.0 : shape[4 * ks + ft];
 #pragma unroll
-                            for (int k = 0; k < kRT; ++k) {
-                                const double2 va = sa[k * kW], vb = sb[k * kW];
-                                acca[k] = fma(va.y, ra1, fma(va.x, ra0, acca[k]));
-                                accb[k] = fma(vb.y, rb1, fma(vb.x, rb0, accb[k]));
-                            }
-                            sa += nrp; sb += nrp; ra += 2 * nR; rb += 2 * nR;
+                    for (int c = 0; c < kMC; ++c)
+                        if (m0 + c < mt) {
+                            double a8v = a8p[c * 8 * ldp + 4 * ks], ahv = ahp[c * 8 * ldp + 4 * ks];
+                            if (!is_es) { a8v *= s; ahv *= s; }
+                            dmma_8x8x4(d8[c][0], d8[c][1], a8v, b8v);
+                            dmma_8x8x4(dh[c][0], dh[c][1], ahv, bhv);
                         }
-                    } else {
-                        const double2* sa = reinterpret_cast<const double2*>(S2) + r0;
-                        const double* ra = D.r_cc + j;
-                        for (int i2 = 0; i2 < npair; ++i2) {
-                            const double ra0 = __ldg(ra), ra1 = __ldg(ra + nR);
-#pragma unroll
-                            for (int k = 0; k < kRT; ++k) {
-                                const double2 va = sa[k * kW];
-                                acca[k] = fma(va.y, ra1, fma(va.x, ra0, acca[k]));
-                            }
-                            sa += nrp; ra += 2 * nR;
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < kRT; ++k) {
-                        const int row = r0 + k * kW;
-                        if (row < nrow && jv) {
-                            const double bgr = (row == 0) ? bgj : bgj * T.wz[row - 1];
-                            rout[row * nR + j] = is_es ? (0.5 * (acca[k] * effa) + 0.5 * (accb[k] * effb)) + 0.5 * bgr
-                                                       : 0.5 * (acca[k] * effa) + 0.5 * bgr;
-                        }
-                    }
                 }
+#pragma unroll
+                for (int c = 0; c < kMC; ++c)
+                    if (m0 + c < mt) {
+                        const int row = 8 * (m0 + c) + fg;
+                        const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
+                        const double r0 = w * fma(f8, d8[c][0], fma(fh, dh[c][0], c0));
+                        const double r1 = w * fma(f8, d8[c][1], fma(fh, dh[c][1], c1));
+                        *reinterpret_cast<double2*>(rout + (size_t)row * ldr) = make_double2(r0, r1);
+                    }
             }
         }
         __syncthreads();
-        // ---- likelihood terms / outputs, one reconstructed bin per thread iteration ------------------
+        // ---- Poisson terms / outputs: the valid (row, reco bin) pairs are dealt out densely, two per
+        //      thread per pass so that two logarithm chains overlap (likelihood_builder.jl:5-20,129-144) --
         double part = 0.0;
         for (int ch = 0; ch < 2; ++ch) {
             const bool is_es = ch == 0;
-            if (is_es ? !D.es_mode : !D.cc_mode) continue;
             const int nR = is_es ? D.n_es : D.n_cc;
+            double* day = is_es ? O.es_day : O.cc_day;
+            double* night = is_es ? O.es_night : O.cc_night;
+            const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
+            if (is_es ? !D.es_mode : !D.cc_mode) {
+                if (MODE != kModeLlh) {   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
+                    const double v = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
+                    for (int o = threadIdx.x; o < nrow * nR; o += blockDim.x) {
+                        if (o < nR) { if (day) day[b * nR + o] = v; }
+                        else if (night) night[b * nZ * nR + (o - nR)] = v;
+                    }
+                }
+                continue;
+            }
             const double* rin = is_es ? rates_es : rates_cc;
             const double* obs = is_es ? D.obs_es : D.obs_cc;
             const double* lobs = is_es ? D.logobs_es : D.logobs_cc;
             const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
-            double* day = is_es ? O.es_day : O.cc_day;
-            double* night = is_es ? O.es_night : O.cc_night;
-            const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
-            // likelihood mode only visits the bins above threshold: nc columns from idx0
+            // likelihood mode only visits the bins above threshold: nc columns from jlo
             const int jlo = (MODE == kModeLlh) ? idx0 : 0, nc = nR - jlo;
             const int dq = (int)blockDim.x / nc, dr = (int)blockDim.x - dq * nc;
             int row = (int)threadIdx.x / nc, jj = (int)threadIdx.x - row * nc;
             while (row < nrow) {
+                int row2 = row + dq, jj2 = jj + dr;          // the element one pass further on
+                if (jj2 >= nc) { jj2 -= nc; ++row2; }
+                const bool two = row2 < nrow;
                 const int j = jlo + jj, od = row * nR + j;
-                const double rate = rin[od];
+                const int jb = jlo + jj2, od2 = two ? row2 * nR + jb : od;
+                const double rate = rin[row * ldr + j], rate2 = rin[(two ? row2 : row) * ldr + (two ? jb : j)];
                 if (MODE == kModeLlh) {
-                    part += poisson_term(rate, obs[od], lobs[od], fl);
+                    const double t1 = poisson_term(rate, obs[od], lobs[od], fl);
+                    const double t2 = poisson_term(rate2, obs[od2], lobs[od2], fl);
+                    part += two ? t1 + t2 : t1;
                 } else {
-                    double v = rate;
-                    if (MODE == kModePerbin) {
-                        v = (j >= idx0 && j < nR - 1) ? perbin_term(rate, obs[od]) : 0.0;
-                        if (oob) v = -INFINITY;
-                    }
-                    if (row == 0) {
-                        if (day) day[(size_t)b * nR + j] = v;
-                    } else if (night) {
-                        night[(size_t)b * nZ * nR + (size_t)(row - 1) * sr + (size_t)j * sj] = v;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !two) break;
+                        const int rr = h ? row2 : row, jx = h ? jb : j, oo = h ? od2 : od;
+                        double v = h ? rate2 : rate;
+                        if (MODE == kModePerbin) {
+                            v = (jx >= idx0 && jx < nR - 1) ? perbin_term(v, obs[oo]) : 0.0;
+                            if (oob) v = -INFINITY;
+                        }
+                        if (rr == 0) {
+                            if (day) day[b * nR + jx] = v;
+                        } else if (night) {
+                            night[b * nZ * nR + (size_t)(rr - 1) * sr + (size_t)jx * sj] = v;
+                        }
                     }
                 }
-                jj += dr; row += dq;
+                jj = jj2 + dr; row = row2 + dq;
                 if (jj >= nc) { jj -= nc; ++row; }
             }
         }
@@ -439,7 +516,6 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
     }
     if (MODE != kModeLlh) return;
     // ---- block reduction (fixed order: deterministic) ----------------------------------------------
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     total = warp_sum(total);
     for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
     if (lane == 0) { red[warp] = total; redf[warp] = fl; }
@@ -447,13 +523,77 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
     if (threadIdx.x == 0) {
         double s = 0.0;
         uint32_t f = 0;
-        for (int w = 0; w < kRatesThreads / 32; ++w) { s += red[w]; f |= redf[w]; }
+        for (int w = 0; w < kWarps; ++w) { s += red[w]; f |= redf[w]; }
         double lnl = -s;
         if (f & SOLAROSC_FLAG_NEG_ERROR) lnl = NAN;
         if (oob) { lnl = -INFINITY; f = SOLAROSC_FLAG_EARTH_OOB; }
         else if (lnl != lnl) f |= (f & SOLAROSC_FLAG_NEG_ERROR) ? 0u : SOLAROSC_FLAG_NONFINITE;
         O.lnl[b] = lnl;
         if (O.flags) O.flags[b] = f;
+    }
+}
+
+// zero the padding of the shared-memory probability tile (rows >= nrow, columns >= n_etrue) of both processes
+__device__ __forceinline__ void fold_zero_padding(double* ps, int nT, int nrow, int ldp) {
+    const int rows = fold_rows(nrow), padc = ldp - nT;
+    for (int proc = 0; proc < 2; ++proc) {
+        double* q = ps + (size_t)proc * rows * ldp;
+        for (int t = threadIdx.x; t < (rows - nrow) * ldp; t += blockDim.x) q[nrow * ldp + t] = 0.0;
+        for (int r = threadIdx.x; r < nrow; r += blockDim.x)
+            for (int c = 0; c < padc; ++c) q[r * ldp + nT + c] = 0.0;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params,
+             const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
+    extern __shared__ double smem[];
+    __shared__ double red[kWarps];
+    __shared__ uint32_t redf[kWarps];
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    double* rbuf = smem;
+    double* p8s = smem + fold_r_doubles(nrow, L.max_ereco);
+    double* phs = p8s + (size_t)rows * ldp;
+    double* scr = p8s + fold_p_doubles(nT, nrow);
+    const size_t b = blockIdx.x;
+    const double* src = osc + (b / L.group) * 2 * nrow * nT;
+    fold_zero_padding(p8s, nT, nrow, ldp);
+    {   // stage the probabilities: (row, i) advance by blockDim.x without a division in the loop
+        const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
+        int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;
+        while (row < nrow) {
+            p8s[row * ldp + i] = src[row * nT + i];
+            phs[row * ldp + i] = src[(nrow + row) * nT + i];
+            i += dr; row += dq;
+            if (i >= nT) { i -= nT; ++row; }
+        }
+    }
+    fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, rbuf, O, red, redf);
+}
+
+// One CTA per oscillation point: K1+K2 into shared memory, then K3+K4+K5 for each of the `group`
+// parameter points sharing it.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params, RatesOut O) {
+    extern __shared__ double smem[];
+    __shared__ double red[kWarps];
+    __shared__ uint32_t redf[kWarps];
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    double* tbl = smem;
+    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * nT;
+    double* p8s = smem + llh_front_doubles(T.n_layers, nT, T.n_cosz, L.max_ereco);
+    double* phs = p8s + (size_t)rows * ldp;
+    double* scr = p8s + fold_p_doubles(nT, nrow);
+    const size_t g = blockIdx.x;
+    const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), L.seg_smem != 0);
+    fold_zero_padding(p8s, nT, nrow, ldp);
+    osc_stage(T, G, params + g * L.group * L.param_stride, 0, nT, nT, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
+    for (int q = 0; q < L.group; ++q) {
+        const size_t b = g * L.group + q;
+        // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
+        fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, smem, O, red, redf);
     }
 }
 

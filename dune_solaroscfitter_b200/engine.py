@@ -168,4 +168,4 @@ class SolarOscEngine:
     def last_timing(self):
         a, b = C.c_float(0), C.c_float(0)
         n = self._L.solarosc_last_timing(self._h, C.byref(a), C.byref(b))
-        return dict(ms_osc=a.value, ms_rates=b.value, launches=n)
+        return dict(ms_osc=a.value, ms_rates=b.value, launches=n, fused=bool(self._L.solarosc_last_fused(self._h)))

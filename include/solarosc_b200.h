@@ -197,6 +197,9 @@ int solarosc_poisson_llh(solarosc_handle *h, const double *expected, const doubl
  * counted, timing or not). */
 int solarosc_set_timing(solarosc_handle *h, int enabled);
 int solarosc_last_timing(solarosc_handle *h, float *ms_osc, float *ms_rates);
+/* 1 if the last likelihood call ran the fused kernel (llh_kernel: ms_osc is its time, ms_rates ~ 0),
+ * 0 if it ran osc_kernel + rates_kernel. */
+int solarosc_last_fused(const solarosc_handle *h);
 
 /* Measured FP64 FMA throughput of the handle's device in TFLOP/s (dependent-chain DFMA probe): the
  * denominator of the FP64 roofline, which MEASURED_PEAKS.json does not carry. */

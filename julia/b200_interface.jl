@@ -1,0 +1,233 @@
+#=
+b200_interface.jl
+
+`ccall` glue between SolarOscFitter's Julia host code and libsolarosc_b200.so, patterned on the
+reference's NuFast glue (src/oscillations/nuFast_interface.jl:1-129): one module, a handle created
+once after setup.jl has built its tables, thin wrappers that keep the call signatures of the
+functions they stand in for.
+
+NOT EXECUTED IN THIS REPOSITORY: the build image has no Julia.  The C ABI it binds is exercised
+from Python (ctypes) by tests/; this file is the binding a SolarOscFitter maintainer drops into
+src/oscillations/ (INTEGRATION.md has the step-by-step wiring and the Makefile rule).
+
+Layout note: Julia arrays are column-major, so the handle is created with `col_major = 1` and every
+matrix (response matrices R[Etrue, Ereco], night data/rates [cosz, Ereco], P_night [cosz, Etrue])
+is passed and returned as it lies in Julia memory.  Batched outputs get the batch index LAST, e.g.
+`ES_night[z, j, b]`.
+=#
+module B200Osc
+
+using Base: @ccall
+
+const libb200 = joinpath(@__DIR__, "libsolarosc_b200.so")
+const Handle = Ptr{Cvoid}
+const handle = Ref{Handle}(C_NULL)
+
+const ABI_VERSION = Int32(1)
+const N_FIXED = 8
+
+# ---- C structs (include/solarosc_b200.h) ---------------------------------------------------------
+struct CDetector
+    es_mode::Int32; cc_mode::Int32
+    n_ereco_es::Int32; n_ereco_cc::Int32
+    index_es::Int32; index_cc::Int32
+    unosc_es_nue_8b::Ptr{Cdouble}; unosc_es_nuother_8b::Ptr{Cdouble}; unosc_cc_8b::Ptr{Cdouble}
+    unosc_es_nue_hep::Ptr{Cdouble}; unosc_es_nuother_hep::Ptr{Cdouble}; unosc_cc_hep::Ptr{Cdouble}
+    log_e_norm::Ptr{Cdouble}
+    resp_es_nue::Ptr{Cdouble}; resp_es_nuother::Ptr{Cdouble}; resp_cc::Ptr{Cdouble}
+    eff_es_nue::Ptr{Cdouble}; eff_es_nuother::Ptr{Cdouble}; eff_cc::Ptr{Cdouble}
+    n_bg_es::Int32; n_bg_cc::Int32
+    raw_bg_es::Ptr{Cdouble}; raw_bg_cc::Ptr{Cdouble}
+    bg_es_sides::Ptr{Int32}; bg_es_par::Ptr{Int32}; bg_cc_par::Ptr{Int32}
+    obs_es_day::Ptr{Cdouble}; obs_es_night::Ptr{Cdouble}; obs_cc_day::Ptr{Cdouble}; obs_cc_night::Ptr{Cdouble}
+end
+
+struct CTables
+    n_etrue::Int32; n_cosz::Int32; n_cosz_sub::Int32; n_layers::Int32; n_solar::Int32; n_det::Int32
+    e_calc::Ptr{Cdouble}
+    seg_start::Ptr{Int32}; seg_layer::Ptr{Int32}; seg_length::Ptr{Cdouble}
+    earth_lookup::Ptr{Cdouble}; exposure_weights::Ptr{Cdouble}
+    avg_ne_8b::Cdouble; avg_ne_hep::Cdouble
+    solar_ne::Ptr{Cdouble}; solar_prod_8b::Ptr{Cdouble}; solar_prod_hep::Ptr{Cdouble}
+    cc_xsec_norm_true::Cdouble
+    det::Ptr{CDetector}
+end
+
+struct CConfig
+    abi_version::Int32; device::Int32; fast::Int32; earth_uncertainty::Int32; col_major::Int32; max_batch::Int32
+end
+
+# Parameter order fixed at create; filled by init_engine
+const det_names = String[]
+const n_layers = Ref(0)
+const n_norms = Tuple{Int,Int}[]
+const earth_unc = Ref(true)
+const xsec_norm_true = Ref(1.0)
+
+f64(x) = collect(Float64, vec(x))
+i32(x) = collect(Int32, vec(x))
+
+"""
+    init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarModel, detector_outputs,
+                detector_configs; fast, earthUncertainty, cc_xsec_norm_true, device=0)
+
+Create the handle from the globals setup.jl has just built (setup.jl:39-66 shared tables, :99-108
+per-detector tables, :160-178 Asimov data and threshold indices).  Call once, after setup.jl's
+detector loop; the counterpart of `nuFastOsc.init_engines` (nuFast_interface.jl:48-64).
+"""
+function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarModel, detector_outputs,
+                     detector_configs; fast::Bool, earthUncertainty::Bool, cc_xsec_norm_true::Float64=1.0,
+                     n_cosz_sub::Int=1, device::Int=0, max_batch::Int=0)
+    keep = Any[]                                   # everything the C structs point into
+    hold(x) = (push!(keep, x); pointer(x))
+
+    seg_start = Int32[0]; seg_layer = Int32[]; seg_length = Float64[]
+    for path in earth_paths, s in path.segments    # makePaths.jl:25-33, detector -> far surface
+        push!(seg_layer, s.index); push!(seg_length, s.length)
+    end
+    for path in earth_paths
+        push!(seg_start, seg_start[end] + length(path.segments))
+    end
+
+    empty!(det_names); empty!(n_norms)
+    dets = CDetector[]
+    for (name, out) in detector_outputs
+        li  = out.likelihood_inputs
+        u   = li.MC_no_osc; r = li.Mreco; bg = li.BG; obs = li.nObserved
+        nes = length(r.eff.ES_nue); ncc = length(r.eff.CC)
+        raw_es = isempty(bg.ES) ? Float64[] : reduce(vcat, f64.(bg.ES))   # component-major
+        raw_cc = isempty(bg.CC) ? Float64[] : reduce(vcat, f64.(bg.CC))
+        push!(det_names, name)
+        push!(n_norms, (count(!=(0), bg.ES_par_counts), count(!=(0), bg.CC_par_counts)))
+        push!(dets, CDetector(
+            li.ES_mode, li.CC_mode, nes, ncc, li.index_ES, li.index_CC,
+            hold(f64(u.ES_nue_8B)), hold(f64(u.ES_nuother_8B)), hold(f64(u.CC_8B)),
+            hold(f64(u.ES_nue_hep)), hold(f64(u.ES_nuother_hep)), hold(f64(u.CC_hep)), hold(f64(u.log_E_norm)),
+            hold(f64(r.ES.nue)), hold(f64(r.ES.nuother)), hold(f64(r.CC)),          # column-major as they are
+            hold(f64(r.eff.ES_nue)), hold(f64(r.eff.ES_nuother)), hold(f64(r.eff.CC)),
+            length(bg.ES), length(bg.CC), hold(raw_es), hold(raw_cc),
+            hold(i32(bg.sides)), hold(i32(bg.ES_par_counts)), hold(i32(bg.CC_par_counts)),
+            hold(f64(obs.ES_day)), hold(f64(obs.ES_night)), hold(f64(obs.CC_day)), hold(f64(obs.CC_night))))
+    end
+    push!(keep, dets)
+
+    tables = CTables(
+        length(E_calc) ÷ 2, length(exposure_weights), n_cosz_sub, length(earth_lookup),
+        fast ? 0 : length(solarModel.n_e), length(dets),
+        hold(f64(E_calc)), hold(seg_start), hold(seg_layer), hold(seg_length),
+        hold(f64(earth_lookup)), hold(f64(exposure_weights)),
+        solarModel.avgNeBoron, solarModel.avgNeHep,
+        hold(f64(solarModel.n_e)), hold(f64(solarModel.prodFractionBoron)), hold(f64(solarModel.prodFractionHep)),
+        cc_xsec_norm_true, pointer(dets))
+    cfg = CConfig(ABI_VERSION, device, fast, earthUncertainty, 1, max_batch)
+    status = Ref{Cint}(0)
+    GC.@preserve keep begin
+        h = @ccall libb200.solarosc_create(Ref(tables)::Ref{CTables}, Ref(cfg)::Ref{CConfig},
+                                           status::Ref{Cint})::Handle
+    end
+    h == C_NULL && error("solarosc_create failed (status $(status[])): " *
+                         unsafe_string(@ccall libb200.solarosc_last_error(C_NULL::Handle)::Cstring))
+    handle[] = h
+    n_layers[] = length(earth_lookup); earth_unc[] = earthUncertainty; xsec_norm_true[] = cc_xsec_norm_true
+    return h
+end
+
+shutdown_engine() = (handle[] != C_NULL && (@ccall libb200.solarosc_destroy(handle[]::Handle)::Cvoid); handle[] = C_NULL; nothing)
+
+n_params() = Int(@ccall libb200.solarosc_n_params(handle[]::Handle)::Cint)
+
+function check(status)
+    status == 0 && return
+    msg = unsafe_string(@ccall libb200.solarosc_last_error(handle[]::Handle)::Cstring)
+    # status 4: a rate <= -1e-3, where poissonLogLikelihood raises (likelihood_statistical.jl:9-14)
+    error("solarosc status $status: $msg")
+end
+
+# Fields of a NamedTuple whose names start with `prefix`, sorted as strings: core.jl:6-15
+by_prefix(p, prefix) = [getfield(p, f) for f in sort([f for f in keys(p) if startswith(string(f), prefix)], by=string)]
+
+"One row of the parameter matrix from the reference's NamedTuple of parameters."
+function pack(p)::Vector{Float64}
+    row = Float64[p.sin2_th12, p.sin2_th13, p.dm2_21, p.integrated_8B_flux, p.integrated_HEP_flux,
+                  hasproperty(p, :cc_xsec_norm) ? p.cc_xsec_norm : xsec_norm_true[],   # propagation_osc.jl:185-187
+                  hasproperty(p, :cc_xsec_tilt) ? p.cc_xsec_tilt : 0.0,
+                  hasproperty(p, :cc_xsec_curv) ? p.cc_xsec_curv : 0.0]
+    earth_unc[] && append!(row, by_prefix(p, "earth_norm_"))
+    for (name, (nes, ncc)) in zip(det_names, n_norms)
+        append!(row, by_prefix(p, "$(name)_ES_bg_norm_")[1:nes])
+        append!(row, by_prefix(p, "$(name)_CC_bg_norm_")[1:ncc])
+    end
+    return row
+end
+
+pack_many(ps::AbstractVector) = reduce(hcat, pack.(ps))        # P x B, column-major == B rows of P doubles
+pack_many(ps::AbstractMatrix{Float64}) = ps                      # already P x B
+
+"""
+    total_llh_batch(params) -> Vector{Float64}
+
+lnL for every parameter point (likelihood_main.jl:30-35 applied to a batch).  `params` is a vector
+of NamedTuples or a P x B matrix.  `-Inf` where an earth norm leaves [0, 2].
+"""
+function total_llh_batch(params; group::Int=1)
+    M = pack_many(params); B = size(M, 2)
+    out = Vector{Float64}(undef, B); flags = Vector{UInt32}(undef, B)
+    GC.@preserve M out flags begin
+        st = group == 1 ?
+            (@ccall libb200.solarosc_eval_llh(handle[]::Handle, pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t,
+                                              pointer(out)::Ptr{Cdouble}, pointer(flags)::Ptr{UInt32})::Cint) :
+            (@ccall libb200.solarosc_eval_llh_grouped(handle[]::Handle, pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t,
+                                                      Csize_t(group)::Csize_t, pointer(out)::Ptr{Cdouble},
+                                                      pointer(flags)::Ptr{UInt32})::Cint)
+        check(st)
+    end
+    return out
+end
+
+"Drop-in for `total_llh(parameters)` (likelihood_main.jl:30-35)."
+total_llh(parameters) = total_llh_batch([parameters])[1]
+
+"""
+    propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc, verbose)
+
+Same signature and 7-tuple as propagation_main.jl:56-157 (exclusive, non-angular branch).  The table
+arguments are the ones the handle was created from; `precomputed_osc` is accepted and not needed.
+"""
+function propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc=nothing, verbose=false)
+    d = findfirst(==(det_flags.det_name), det_names) - 1
+    r = expected_rates_batch([params], d)
+    return r.ES_day[:, 1], r.CC_day[:, 1], r.ES_night[:, :, 1], r.CC_night[:, :, 1], r.BG_ES_tot[:, 1], r.BG_CC_tot[:, 1], nothing
+end
+
+function expected_rates_batch(params, det::Int=0; nz::Int, nes::Int, ncc::Int)
+    M = pack_many(params); B = size(M, 2)
+    ES_day = Array{Float64}(undef, nes, B); ES_night = Array{Float64}(undef, nz, nes, B)
+    CC_day = Array{Float64}(undef, ncc, B); CC_night = Array{Float64}(undef, nz, ncc, B)
+    BG_ES = Array{Float64}(undef, nes, B);  BG_CC = Array{Float64}(undef, ncc, B)
+    GC.@preserve M ES_day ES_night CC_day CC_night BG_ES BG_CC begin
+        check(@ccall libb200.solarosc_eval_rates(handle[]::Handle, Cint(det)::Cint, pointer(M)::Ptr{Cdouble},
+            Csize_t(B)::Csize_t, pointer(ES_day)::Ptr{Cdouble}, pointer(ES_night)::Ptr{Cdouble},
+            pointer(CC_day)::Ptr{Cdouble}, pointer(CC_night)::Ptr{Cdouble}, pointer(BG_ES)::Ptr{Cdouble},
+            pointer(BG_CC)::Ptr{Cdouble})::Cint)
+    end
+    return (ES_day=ES_day, CC_day=CC_day, ES_night=ES_night, CC_night=CC_night, BG_ES_tot=BG_ES, BG_CC_tot=BG_CC)
+end
+
+"""
+    compute_shared_osc_probs(params, solarModel)
+
+8-field NamedTuple of propagation_osc.jl:146-155 (night arrays are (n_cosz, n_Etrue)).
+"""
+function compute_shared_osc_probs(params, solarModel; nz::Int, nT::Int)
+    M = pack_many([params])
+    d8 = Vector{Float64}(undef, nT); n8 = Matrix{Float64}(undef, nz, nT)
+    dh = Vector{Float64}(undef, nT); nh = Matrix{Float64}(undef, nz, nT)
+    GC.@preserve M d8 n8 dh nh begin
+        check(@ccall libb200.solarosc_eval_oscprobs(handle[]::Handle, pointer(M)::Ptr{Cdouble}, Csize_t(1)::Csize_t,
+            pointer(d8)::Ptr{Cdouble}, pointer(n8)::Ptr{Cdouble}, pointer(dh)::Ptr{Cdouble}, pointer(nh)::Ptr{Cdouble})::Cint)
+    end
+    return (nue_8B_day=d8, nue_8B_night=n8, nue_hep_day=dh, nue_hep_night=nh,
+            nuother_8B_day=1 .- d8, nuother_8B_night=1 .- n8, nuother_hep_day=1 .- dh, nuother_hep_night=1 .- nh)
+end
+
+end # module B200Osc
