@@ -113,15 +113,16 @@ def cpu_sample(t, params, seconds_budget: float = 12.0):
     """Time the C oracle (all host threads) on a bounded, evenly spaced sample of the workload."""
     from oracle import oracle_c, oracle_np
     co = oracle_c.COracle(t, oracle_np.asimov_data(t))
-    cores = oracle_c.max_threads()
+    # every host core the process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS, not OpenMP)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     probe = params[:: max(1, len(params) // (4 * cores))][: 4 * cores]
     t0 = time.perf_counter()
-    co.eval_llh(probe)
+    co.eval_llh(probe, n_threads=cores)
     rate = len(probe) / (time.perf_counter() - t0)
     n = int(max(cores, min(len(params), rate * seconds_budget)))
     sample = np.ascontiguousarray(params[:: max(1, len(params) // n)][:n])
     t0 = time.perf_counter()
-    lnl, _ = co.eval_llh(sample)
+    lnl, _ = co.eval_llh(sample, n_threads=cores)
     dt = time.perf_counter() - t0
     return len(sample) / dt, cores, f"{len(sample)} evenly spaced points of the {len(params)}-point scan, {dt:.1f} s", lnl, sample
 
@@ -333,7 +334,7 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "e2e_equals_device_result": same,
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU leg runs at N = 1 only
         v, cores, desc, lnl_cpu, sample = cpu_sample(t, params)
         gpu_on_sample = eng.eval_llh(sample)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
