@@ -76,6 +76,7 @@ struct solarosc_handle {
     size_t osc_smem_limit = 200 * 1024;
     size_t fused_smem = 0, seg_bytes = 0;
     bool fused_seg = false;
+    bool rates_ok = true;
     bool fused_ok = false;
     std::mutex mu;
     std::string err;
@@ -289,7 +290,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
     // Points per internal chunk.  The oscillation-probability workspace (osc_pt doubles per point)
     // is the only large buffer; the default keeps it near 1 GiB of the 180 GB of HBM.
-    h->chunk = c->max_batch > 0 ? c->max_batch : (int)std::max<size_t>(1024, std::min<size_t>(32768, ((size_t)1 << 30) / (osc_pt * sizeof(double))));
+    h->chunk = c->max_batch > 0 ? c->max_batch : (int)std::max<size_t>(16, std::min<size_t>(32768, ((size_t)1 << 30) / (osc_pt * sizeof(double))));
     for (int i = 0; i < 2; ++i) {
         h->d_params2[i] = h->dalloc<double>((size_t)h->chunk * h->P);
         h->d_lnl2[i] = h->dalloc<double>(h->chunk);
@@ -298,10 +299,14 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     h->d_params = h->d_params2[0];
     h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
     const size_t rs = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
-    if (rs > prop.sharedMemPerBlockOptin) throw ArgFail{"binning too large for the fold's shared-memory tile"};
-    CK(cudaFuncSetAttribute(rates_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-    CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
-    CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    // A binning whose probability tile does not fit one SM's shared memory (e.g. the 1000 x 1000 zenith x
+    // energy convergence sweep) can still use the oscillation-stage entry points; the fold needs the tile.
+    h->rates_ok = rs <= prop.sharedMemPerBlockOptin;
+    if (h->rates_ok) {
+        CK(cudaFuncSetAttribute(rates_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     // the fused kernel needs the whole energy axis of one point in one CTA
     h->fused_smem = llh_smem_bytes(T.n_layers, T.n_etrue, T.n_cosz, h->max_ereco);
@@ -377,6 +382,7 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
 }
 
 void check_data(solarosc_handle* h, int det_only) {
+    if (!h->rates_ok) throw ArgFail{"binning too large for the fold's shared-memory tile: only the oscillation-stage calls are available"};
     for (int d = 0; d < h->T.n_det; ++d)
         if ((det_only < 0 || d == det_only) && !h->has_data[d])
             throw ArgFail{"observed data not set for a detector (pass obs_* at create or call solarosc_set_data)"};
@@ -462,6 +468,7 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     REQUIRE(params, "params must not be NULL");
     REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
     if (mode == kModePerbin) check_data(h, det);
+    REQUIRE(h->rates_ok, "binning too large for the fold's shared-memory tile");
     const int nZ = h->T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
     const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
     const int step = std::max(1, std::min(h->chunk, 1024));

@@ -1,0 +1,134 @@
+"""GPU parity on the other BASELINE.json configurations.
+
+C2 (the LLH scan) is bench.py's workload; these are the parity-test cases.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def engine(tables, asimov):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    with SolarOscEngine(tables, data=asimov) as e:
+        yield e
+
+
+# ---- C1: single point at truth + the literal tests/benchmark_likelihoods.jl shapes --------------------------
+def test_c1_single_point_at_truth(engine, tables):
+    from oracle import oracle_c
+    got = engine.eval_llh(np.asarray(tables["truth"], dtype=float))
+    assert got.shape == (1,) and abs(got[0]) < 1e-6
+
+
+def test_c1_fake_200x200_likelihood_shape(engine):
+    """benchmark_likelihoods.jl:23-74: 200 ES + 200 CC bins x (1 day + 200 zenith rows) = 80 400 Poisson terms,
+    rates filled with one scale, data U{10..50}."""
+    from oracle import oracle_c
+    rng = np.random.default_rng(17)
+    m = rng.integers(10, 51, (4, 80400)).astype(float)
+    e = np.repeat(np.array([[1.0], [17.5], [30.0], [49.0]]), 80400, axis=1)
+    got = engine.poisson_llh(e, m)
+    ref = np.array([oracle_c.COracle.poisson(e[i], m[i])[0] for i in range(4)])
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+
+
+# ---- C3: MCMC-style batches of independent prior draws ------------------------------------------------------------
+@pytest.mark.parametrize("batch", [10, 4096])
+def test_c3_prior_draw_batches(engine, tables, asimov, draw, batch):
+    from oracle import oracle_c
+    p = draw(tables, batch, seed=1000 + batch)
+    ref, rfl = oracle_c.COracle(tables, asimov).eval_llh(p)
+    got, fl = engine.eval_llh(p, return_flags=True)
+    assert np.array_equal(fl, rfl)
+    assert np.max(np.abs(2 * got - 2 * ref)) < 1e-6
+
+
+# ---- C4: Earth-density systematics on dense zenith x energy grids ---------------------------------------------------
+def _dense(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def _earth_draws(t, n, seed):
+    rng = np.random.default_rng(seed)
+    p = np.tile(np.asarray(t["truth"], dtype=float), (n, 1))
+    p[:, 8:14] = np.clip(rng.normal(1.0, 0.12, (n, 6)), 0.0, 2.0)      # truncN(1, 0.12; 0, 2)
+    p[0, 0], p[0, 2] = 0.4, 2e-4                                       # checkOscGridConvergence.jl:40-42 worst case
+    return p
+
+
+def test_c4_dense_200x200_matches_oracle():
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    from oracle import oracle_c
+    t = _dense("tables_dense200_osc.npz")
+    p = _earth_draws(t, 3, 5)
+    ref_osc, ref_p1e = oracle_c.COracle(t, None).eval_oscprobs(p, want_p1e=True)
+    with SolarOscEngine(t) as e:
+        p1e = e.eval_p1e(p)
+        osc = e.eval_oscprobs(p)
+    assert p1e.shape == (3, 200, 200)
+    assert np.max(np.abs(p1e - ref_p1e)) < 5e-12
+    assert np.max(np.abs(osc["nue_8B_night"] - ref_osc[:, 0, 1:])) < 5e-12
+    assert np.max(np.abs(osc["nue_hep_day"] - ref_osc[:, 1, 0])) < 1e-14
+
+
+def test_c4_dense_1000x1000_sweep():
+    """The 1000 cos z x 1000 E grid of utils/checkOscGridConvergence.jl: too large for the fold's
+    shared-memory tile, so only the oscillation-stage calls are offered -- and they match the oracle."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine, SolarOscError
+    from oracle import oracle_c
+    t = _dense("tables_dense1000_osc.npz")
+    p = _earth_draws(t, 2, 9)
+    ref_osc, ref_p1e = oracle_c.COracle(t, None).eval_oscprobs(p[:1], want_p1e=True)
+    with SolarOscEngine(t) as e:
+        p1e = e.eval_p1e(p)
+        assert p1e.shape == (2, 1000, 1000)
+        assert np.max(np.abs(p1e[0] - ref_p1e[0])) < 5e-12
+        osc = e.eval_oscprobs(p[:1])
+        assert np.max(np.abs(osc["nue_8B_night"][0] - ref_osc[0, 0, 1:])) < 5e-12
+        v = p[1].copy(); v[8:14] = 0.0                                  # vacuum: size-independent property
+        assert np.max(np.abs(e.eval_p1e(v) - (1 - v[0]) * (1 - v[1]))) < 1e-14
+        with pytest.raises(SolarOscError):
+            e.eval_llh(p)
+
+
+def test_c4_night_only_cc_default_grid(tables, draw):
+    """Night-only CC likelihood with earth-norm draws, B = 4096: ES off, day data zero-weighted by comparing
+    against the oracle configured the same way."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    from oracle import oracle_c, oracle_np
+    data = oracle_np.asimov_data(tables)
+    p = np.tile(np.asarray(tables["truth"], dtype=float), (4096, 1))
+    p[:, 8:14] = np.clip(np.random.default_rng(3).normal(1.0, 0.12, (4096, 6)), 0.0, 2.0)
+    ref, _ = oracle_c.COracle(tables, data, es_mode=False).eval_llh(p)
+    with SolarOscEngine(tables, data=data, es_mode=False) as e:
+        got = e.eval_llh(p)
+        r = e.eval_rates(p[:2])
+    assert np.max(np.abs(2 * got - 2 * ref)) < 1e-6
+    assert np.all(r["ES_day"] == 0) and np.all(r["ES_night"] == 0)     # propagation_reco.jl:12-15
+
+
+# ---- C5: derived quantities over a stored chain ---------------------------------------------------------------------------
+def test_c5_day_night_asymmetry_and_moments(engine, tables, asimov, draw):
+    """derive_variables_from_chain.jl:231-258,285-444: asymmetries from thresholded sums, weighted rate moments."""
+    from dune_solaroscfitter_b200.derived import day_night_asymmetry, weighted_moments
+    from oracle import oracle_c
+    p = draw(tables, 64, seed=77)
+    w = np.random.default_rng(1).integers(1, 5, 64).astype(float)
+    got = engine.eval_rates(p)
+    ref = oracle_c.COracle(tables, asimov).eval_rates(p)
+    for ch, idx in (("ES", int(tables["index_es"])), ("CC", int(tables["index_cc"]))):
+        a = day_night_asymmetry(got[ch + "_day"], got[ch + "_night"], got["BG_" + ch + "_tot"], idx)
+        b = day_night_asymmetry(ref[ch + "_day"], ref[ch + "_night"], ref["BG_" + ch + "_tot"], idx)
+        assert np.max(np.abs(a - b)) < 1e-9
+        m1, m2 = weighted_moments(got[ch + "_night"], w, idx)
+        r1, r2 = weighted_moments(ref[ch + "_night"], w, idx)
+        assert np.max(np.abs(m1 - r1) / np.maximum(np.abs(r1), 1e-300)) < 1e-9
+        assert np.max(np.abs(m2 - r2) / np.maximum(np.abs(r2), 1e-300)) < 1e-9
+    pb = engine.eval_perbin(p[:4])
+    assert pb["CC_night"].shape == (4, 50, 30) and np.all(pb["CC_night"][:, :, -1] == 0)
