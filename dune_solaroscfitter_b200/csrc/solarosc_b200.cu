@@ -306,6 +306,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(rates_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(rates_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     // the fused kernel needs the whole energy axis of one point in one CTA
@@ -315,7 +316,10 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     h->fused_seg = h->fused_smem + h->seg_bytes <= (h->fused_smem * 2 <= 220 * 1024 ? 110 * 1024 : prop.sharedMemPerBlockOptin);
     if (h->fused_seg) h->fused_smem += h->seg_bytes;
     h->fused_ok = h->fused_smem <= prop.sharedMemPerBlockOptin;
-    if (h->fused_ok) CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+    if (h->fused_ok) {
+        CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+    }
 }
 
 // ---- launches ------------------------------------------------------------------------------------
@@ -357,6 +361,7 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     const RatesLaunch L = rates_launch(h, n, group, det_only);
     const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
     if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    else if (mode == kModeAsym) rates_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     else rates_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     CK(cudaGetLastError());
@@ -365,11 +370,13 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
 
 // lnL of n points; the fused kernel when the batch fills the GPU, otherwise the energy-split
 // oscillation kernel followed by the fold kernel.  Returns true when the fused kernel ran.
-bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid) {
+bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid,
+                int mode = kModeLlh, int det_only = -1) {
     const int n_osc = n / group;
     if (h->fused_ok && h->use_fused && n_osc >= h->sm_count) {
-        const RatesLaunch L = rates_launch(h, n, group, -1);
-        llh_kernel<kModeLlh><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        const RatesLaunch L = rates_launch(h, n, group, det_only);
+        if (mode == kModeLlh) llh_kernel<kModeLlh><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        else llh_kernel<kModeAsym><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         CK(cudaGetLastError());
         ++h->launches;
         if (mid) CK(cudaEventRecord(mid, st));
@@ -377,7 +384,7 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
     }
     launch_osc(h, d_params, n_osc, group, nullptr, st);
     if (mid) CK(cudaEventRecord(mid, st));
-    launch_rates(h, d_params, n, group, kModeLlh, -1, O, st);
+    launch_rates(h, d_params, n, group, mode, det_only, O, st);
     return false;
 }
 
@@ -595,6 +602,28 @@ int solarosc_eval_perbin(solarosc_handle* h, int det, const double* params, size
     return guarded(h, [&]() {
         return n == 0 ? (int)SOLAROSC_OK
                       : eval_arrays_host(h, det, kModePerbin, params, n, es_day, es_night, cc_day, cc_night, nullptr, nullptr);
+    });
+}
+
+int solarosc_eval_asymmetry(solarosc_handle* h, int det, const double* params, size_t n, double* asym_es, double* asym_cc) {
+    return guarded(h, [&]() {
+        if (n == 0) return (int)SOLAROSC_OK;
+        REQUIRE(params, "params must not be NULL");
+        REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
+        REQUIRE(h->rates_ok, "binning too large for the fold's shared-memory tile");
+        h->ensure_scratch((size_t)2 * h->chunk * sizeof(double));
+        h->launches = 0;
+        for (size_t b0 = 0; b0 < n; b0 += h->chunk) {
+            const int nb = (int)std::min<size_t>(h->chunk, n - b0);
+            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            RatesOut O{};
+            O.asym_es = h->d_scratch; O.asym_cc = h->d_scratch + h->chunk;
+            launch_llh(h, h->d_params, nb, 1, O, h->stream, nullptr, kModeAsym, det);
+            if (asym_es) CK(cudaMemcpyAsync(asym_es + b0, O.asym_es, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (asym_cc) CK(cudaMemcpyAsync(asym_cc + b0, O.asym_cc, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        return (int)SOLAROSC_OK;
     });
 }
 

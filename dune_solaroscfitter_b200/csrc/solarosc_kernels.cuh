@@ -39,7 +39,7 @@ struct OscLaunch {
     int seg_smem;     // path tables staged in shared memory behind the eigen table
 };
 
-enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2 };
+enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2, kModeAsym = 3 };
 
 struct RatesLaunch {
     int n_points;
@@ -54,6 +54,7 @@ struct RatesLaunch {
 struct RatesOut {
     double* lnl; uint32_t* flags;
     double *es_day, *es_night, *cc_day, *cc_night, *bg_es, *bg_cc;
+    double *asym_es, *asym_cc;   // kModeAsym: day-night asymmetry per point and channel
 };
 
 // ---- shared-memory geometry ------------------------------------------------------------------------
@@ -74,7 +75,7 @@ __host__ __device__ inline int fold_ldp(int n_etrue) {
 __host__ __device__ inline int fold_rows(int nrow) { return 8 * ((nrow + 7) / 8); }
 __host__ __device__ inline size_t fold_p_doubles(int n_etrue, int nrow) { return (size_t)2 * fold_rows(nrow) * fold_ldp(n_etrue); }
 __host__ __device__ inline size_t fold_scratch_doubles(int n_etrue, int max_ereco) {
-    return (size_t)4 * fold_kt(n_etrue) + (size_t)2 * 8 * ((max_ereco + 7) / 8) + 8;
+    return (size_t)4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8) + 8;
 }
 // folded rates of both channels, [2][rows padded to 8][reco bins padded to 8]
 __host__ __device__ inline size_t fold_r_doubles(int nrow, int max_ereco) {
@@ -327,6 +328,18 @@ __device__ __forceinline__ double perbin_term(double raw_e, double m) {
     return -raw_e;
 }
 
+// block-wide sum, valid on thread 0 (two barriers; red holds one double per warp)
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kWarps; ++w) s += red[w];
+    return s;
+}
+
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe.  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
 // D[l>>2][2*(l&3) + {0,1}].
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
@@ -371,6 +384,8 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         const double* pd = p + D.param_off;
         const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
         double* cst_cc = cst_es + 8 * nte;
+        double* bgs_es = cst_cc + 8 * ntc;       // summed backgrounds per reco bin (asymmetry mode)
+        double* bgs_cc = bgs_es + 8 * nte;
         __syncthreads();   // the previous point / detector is done with the scratch
         // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
         //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
@@ -394,6 +409,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                     if (MODE == kModeRates && O.bg_es) O.bg_es[b * D.n_es + j] = acc;
                 }
                 cst_es[j] = c;
+                if (MODE == kModeAsym) bgs_es[j] = acc;
             } else {
                 const int jc = j - 8 * nte;
                 if (jc < D.n_cc) {
@@ -405,6 +421,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                     if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
                 }
                 cst_cc[jc] = c;
+                if (MODE == kModeAsym) bgs_cc[jc] = acc;
             }
         }
         __syncthreads();
@@ -463,7 +480,10 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
             double* night = is_es ? O.es_night : O.cc_night;
             const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
             if (is_es ? !D.es_mode : !D.cc_mode) {
-                if (MODE != kModeLlh) {   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
+                if (MODE == kModeAsym) {
+                    double* out = is_es ? O.asym_es : O.asym_cc;
+                    if (out && threadIdx.x == 0) out[b] = 0.0;
+                } else if (MODE != kModeLlh) {   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
                     const double v = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
                     for (int o = threadIdx.x; o < nrow * nR; o += blockDim.x) {
                         if (o < nR) { if (day) day[b * nR + o] = v; }
@@ -477,7 +497,8 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
             const double* lobs = is_es ? D.logobs_es : D.logobs_cc;
             const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
             // likelihood mode only visits the bins above threshold: nc columns from jlo
-            const int jlo = (MODE == kModeLlh) ? idx0 : 0, nc = nR - jlo;
+            const int jlo = (MODE == kModeLlh || MODE == kModeAsym) ? idx0 : 0, nc = nR - jlo;
+            double dsum = 0.0, nsum = 0.0;          // asymmetry mode: day / night totals above threshold
             const int dq = (int)blockDim.x / nc, dr = (int)blockDim.x - dq * nc;
             int row = (int)threadIdx.x / nc, jj = (int)threadIdx.x - row * nc;
             while (row < nrow) {
@@ -491,6 +512,9 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                     const double t1 = poisson_term(rate, obs[od], lobs[od], fl);
                     const double t2 = poisson_term(rate2, obs[od2], lobs[od2], fl);
                     part += two ? t1 + t2 : t1;
+                } else if (MODE == kModeAsym) {
+                    if (row == 0) dsum += rate; else nsum += rate;
+                    if (two) { if (row2 == 0) dsum += rate2; else nsum += rate2; }
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -510,6 +534,19 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                 }
                 jj = jj2 + dr; row = row2 + dq;
                 if (jj >= nc) { jj -= nc; ++row; }
+            }
+            if (MODE == kModeAsym) {
+                // derive_variables_from_chain.jl:236-258: half of the background above threshold is taken off
+                // the day total and half off the night total; a zero denominator gives 0
+                const double dtot = block_sum(dsum, red), ntot = block_sum(nsum, red);
+                if (threadIdx.x == 0) {
+                    const double* bgs = is_es ? bgs_es : bgs_cc;
+                    double bg = 0.0;
+                    for (int j = idx0; j < nR; ++j) bg += bgs[j];
+                    const double dd = dtot - 0.5 * bg, nn = ntot - 0.5 * bg, den = dd + nn;
+                    double* out = is_es ? O.asym_es : O.asym_cc;
+                    if (out) out[b] = (den == 0.0) ? 0.0 : 2.0 * (dd - nn) / den;
+                }
             }
         }
         total += part;

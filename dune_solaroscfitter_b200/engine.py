@@ -122,6 +122,13 @@ class SolarOscEngine:
                                                  _dp(r["CC_day"]), _dp(r["CC_night"])))
         return r
 
+    def eval_asymmetry(self, params, det: int = 0):
+        """Per-point day-night asymmetries (ES, CC), reduced on the device."""
+        p = self._params(params)
+        a_es, a_cc = np.empty(len(p)), np.empty(len(p))
+        self._check(self._L.solarosc_eval_asymmetry(self._h, det, _dp(p), len(p), _dp(a_es), _dp(a_cc)))
+        return a_es, a_cc
+
     def eval_oscprobs(self, params) -> Dict[str, np.ndarray]:
         p = self._params(params)
         n, nT = len(p), self.n_etrue

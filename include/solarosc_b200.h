@@ -27,6 +27,7 @@
  *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
  *                          propagation_main.jl:56-157 (exclusive, non-angular branch)
  *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
+ *   solarosc_eval_asymmetry the per-sample D/N asymmetry of derive_variables_from_chain.jl:236-258
  *   solarosc_eval_oscprobs compute_shared_osc_probs, propagation_main.jl:47-54
  *   solarosc_eval_p1e      Osc.NumOsc.Fast.osc_prob_earth, osc.jl:448-477
  *   solarosc_poisson_llh   poissonLogLikelihood, likelihood_statistical.jl:1-28
@@ -169,6 +170,12 @@ int solarosc_eval_rates(solarosc_handle *h, int det, const double *params, size_
  * everywhere for a point whose earth norms are out of bounds). */
 int solarosc_eval_perbin(solarosc_handle *h, int det, const double *params, size_t n_points, double *es_day,
                          double *es_night, double *cc_day, double *cc_night);
+
+/* Day-night asymmetry 2(D - N)/(D + N) of detector det per point and channel, from the background-subtracted
+ * rate totals above threshold (derive_variables_from_chain.jl:236-258), reduced on the device: 16 bytes per
+ * point come back instead of the 49 kB of rate arrays.  Either output may be NULL. */
+int solarosc_eval_asymmetry(solarosc_handle *h, int det, const double *params, size_t n_points, double *asym_es,
+                            double *asym_cc);
 
 /* nu_e survival probabilities at analysis resolution: day [n][n_etrue], night [n][n_cosz][n_etrue]
  * (col_major: [n][n_etrue][n_cosz]); nu_other = 1 - nu_e. */

@@ -130,5 +130,14 @@ def test_c5_day_night_asymmetry_and_moments(engine, tables, asimov, draw):
         r1, r2 = weighted_moments(ref[ch + "_night"], w, idx)
         assert np.max(np.abs(m1 - r1) / np.maximum(np.abs(r1), 1e-300)) < 1e-9
         assert np.max(np.abs(m2 - r2) / np.maximum(np.abs(r2), 1e-300)) < 1e-9
+    # the same asymmetries reduced on the device (16 bytes per sample instead of the rate arrays)
+    a_es, a_cc = engine.eval_asymmetry(p)
+    assert np.max(np.abs(a_es - day_night_asymmetry(ref["ES_day"], ref["ES_night"], ref["BG_ES_tot"], int(tables["index_es"])))) < 1e-9
+    assert np.max(np.abs(a_cc - day_night_asymmetry(ref["CC_day"], ref["CC_night"], ref["BG_CC_tot"], int(tables["index_cc"])))) < 1e-9
+    big = draw(tables, 600, seed=78)          # large enough for the fused kernel
+    b_es, b_cc = engine.eval_asymmetry(big)
+    rb = engine.eval_rates(big)
+    assert np.max(np.abs(b_cc - day_night_asymmetry(rb["CC_day"], rb["CC_night"], rb["BG_CC_tot"], int(tables["index_cc"])))) < 1e-10
+    assert np.max(np.abs(b_es - day_night_asymmetry(rb["ES_day"], rb["ES_night"], rb["BG_ES_tot"], int(tables["index_es"])))) < 1e-10  # background-dominated: rounding order shows
     pb = engine.eval_perbin(p[:4])
     assert pb["CC_night"].shape == (4, 50, 30) and np.all(pb["CC_night"][:, :, -1] == 0)
