@@ -323,7 +323,9 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
 }
 
 // ---- launches ------------------------------------------------------------------------------------
-void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point_step, double* d_p1e, cudaStream_t st) {
+void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point_step, double* d_p1e, cudaStream_t st,
+                int n_var = 1, double* d_out = nullptr) {
+    n_osc *= n_var;   // every variant is an output slot of its own
     const DevTables& T = h->T;
     // coarse bins per CTA: the whole spectrum when the batch alone fills the GPU, otherwise split the
     // energy axis so that about two CTAs per SM exist; never more than shared memory holds
@@ -337,8 +339,8 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     size_t sm = osc_smem_bytes(T.n_layers, cb);
     const bool seg = sm + h->seg_bytes <= std::min<size_t>(h->osc_smem_limit, 110 * 1024);
     if (seg) sm += h->seg_bytes;
-    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0};
-    osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, h->d_osc, d_p1e);
+    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0, n_var};
+    osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, d_out ? d_out : h->d_osc, d_p1e);
     CK(cudaGetLastError());
     ++h->launches;
 }

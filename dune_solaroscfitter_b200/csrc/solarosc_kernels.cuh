@@ -37,6 +37,7 @@ struct OscLaunch {
     int param_stride; // doubles between consecutive points' parameter rows
     int point_step;   // parameter row of oscillation point g is g*point_step (grouped evaluation)
     int seg_smem;     // path tables staged in shared memory behind the eigen table
+    int n_var;        // 1, or 1 + 2*n_dir: every point is followed by its +/- finite-difference variants
 };
 
 enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2, kModeAsym = 3 };
@@ -95,6 +96,13 @@ __host__ __device__ inline size_t llh_smem_bytes(int n_layers, int n_etrue, int 
                              fold_scratch_doubles(n_etrue, max_ereco));
 }
 
+// Oscillation-stage directions of the gradient path: sin2_th12, sin2_th13, dm2_21, then earth_norm_k.
+__host__ __device__ inline int grad_dir_col(int d) { return d < 3 ? d : SOLAROSC_N_FIXED_PARAMS + (d - 3); }
+// Central-difference half-step of column col.  The probabilities are smooth and carry ~1e-13 of rounding
+// noise, so a step of 1e-6 (absolute; relative 1e-7 for dm2_21, whose phases multiply it by ~1e7) keeps
+// both truncation and noise near 1e-8 of the derivative.
+__host__ __device__ inline double grad_step(int col, const double* p) { return col == 2 ? 1e-7 * p[2] : 1e-6; }
+
 // ------------------------------------------------------------------------------------------
 // K1 + K2.  `sink.put(row, i, p8, ph)` receives the block-averaged nu_e survival probabilities of
 // coarse energy bin i for row 0 (day) and rows 1 + z (night zenith bin z).  Ends without a barrier.
@@ -144,12 +152,15 @@ __device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double
 
 template <class Sink>
 __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G, const double* __restrict__ p, int i0, int cb,
-                                          int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink) {
+                                          int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink,
+                                          int vcol = -1, double vdelta = 0.0) {
+    // (vcol, vdelta): parameter column shifted by vdelta -- the finite-difference variants of the gradient path
     const int ne = 2 * cb;   // fine energies handled here
     const int nl = T.n_layers;
     // mixing parameters (reference propagation_osc.jl:30-36: theta = asin(sqrt(clamp(sin2, 0, 1))))
-    const double s12sq = fmin(fmax(p[0], 0.0), 1.0), s13sq = fmin(fmax(p[1], 0.0), 1.0);
-    const double dm21 = p[2];
+    const double s12sq = fmin(fmax(p[0] + (vcol == 0 ? vdelta : 0.0), 0.0), 1.0);
+    const double s13sq = fmin(fmax(p[1] + (vcol == 1 ? vdelta : 0.0), 0.0), 1.0);
+    const double dm21 = p[2] + (vcol == 2 ? vdelta : 0.0);
     const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq;
     const double c13 = sqrt(c13sq);
     const double u1 = sqrt(c12sq) * c13, u2 = sqrt(s12sq) * c13, u3 = sqrt(s13sq);
@@ -160,7 +171,7 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     for (int t = threadIdx.x; t < ne * nl; t += blockDim.x) {
         const int k = t / ne, el = t - k * ne;
         const double e = T.e_calc[2 * i0 + el];
-        const double norm = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + k] : 1.0;
+        const double norm = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + k] + (vcol == SOLAROSC_N_FIXED_PARAMS + k ? vdelta : 0.0) : 1.0;
         const double a = norm * T.earth_lookup[k] * e;   // lookup = earth_norm .* earth_lookup (propagation_osc.jl:60)
         const int slot = (el & 1) * cbs + (el >> 1);
         make_entry(dm21, a, e, u1, u2, u3, tbl + ((size_t)k * 2 * cbs + slot) * kEntry);
@@ -265,8 +276,16 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
            double* __restrict__ osc_out /* [n_points][2][1+n_cosz][n_etrue] */,
            double* __restrict__ p1e_out /* [n_points][n_paths][n_e] or nullptr */) {
     extern __shared__ double smem[];
-    const int g = blockIdx.x / L.n_chunks;
+    const int g = blockIdx.x / L.n_chunks;               // output slot: (point, variant)
     const int chunk = blockIdx.x - g * L.n_chunks;
+    const int point = g / L.n_var, var = g - point * L.n_var;
+    const double* p = params + (size_t)point * L.point_step * L.param_stride;
+    int vcol = -1;
+    double vdelta = 0.0;
+    if (var > 0) {
+        vcol = grad_dir_col((var - 1) >> 1);
+        vdelta = ((var - 1) & 1) ? -grad_step(vcol, p) : grad_step(vcol, p);
+    }
     const int i0 = chunk * L.cb;                         // first coarse energy bin of this CTA
     const int cb = min(L.cb, T.n_etrue - i0);            // coarse bins handled here
     const int nrow = 1 + T.n_cosz;
@@ -274,8 +293,7 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     double* msw = smem + (size_t)kEntry * T.n_layers * 2 * L.cb;   // [2 proc][2 what][2 parity][cbs]
     const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_layers, L.cb), L.seg_smem != 0);
     GlobalSink sink{osc_out + (size_t)g * 2 * nrow * T.n_etrue, osc_out + ((size_t)g * 2 + 1) * nrow * T.n_etrue, T.n_etrue};
-    osc_stage(T, G, params + (size_t)g * L.point_step * L.param_stride, i0, cb, L.cb, tbl, msw,
-              p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr, sink);
+    osc_stage(T, G, p, i0, cb, L.cb, tbl, msw, p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr, sink, vcol, vdelta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -345,6 +363,58 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Forward fold on the FP64 tensor pipe: one (channel, 8-bin column block) per warp pass; kMC row tiles stay
+// in flight, so every k-step issues 2*kMC independent DMMAs behind two B-fragment loads.  Writes the
+// expected rates rates[row][j] = w_row (F8 G8 + Fh Gh + cst[j]) of both channels to shared memory.
+__device__ __forceinline__ void fold_forward(const DevTables& T, const DevDetector& D, double f8, double fh,
+                                             const double* p8s, const double* phs, int ldp, const double* shape,
+                                             const double* cst_es, const double* cst_cc, double* rates_es,
+                                             double* rates_cc, int ldr) {
+    const int nrow = 1 + T.n_cosz, kt = fold_kt(T.n_etrue), mt = (nrow + 7) / 8;
+    const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fg = lane >> 2, ft = lane & 3;
+    for (int task = warp; task < nte + ntc; task += kWarps) {
+        const bool is_es = task < nte;
+        if (is_es ? !D.es_mode : !D.cc_mode) continue;
+        const int n0 = 8 * (is_es ? task : task - nte);
+        const int ldb = 8 * (is_es ? nte : ntc);
+        const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
+        const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
+        const int j0 = n0 + 2 * ft;                                      // this lane's two columns
+        const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
+        double* rout = (is_es ? rates_es : rates_cc) + j0;
+        for (int m0 = 0; m0 < mt; m0 += kMC) {
+            double d8[kMC][2], dh[kMC][2];
+#pragma unroll
+            for (int c = 0; c < kMC; ++c) { d8[c][0] = d8[c][1] = dh[c][0] = dh[c][1] = 0.0; }
+            const double* a8p = p8s + (8 * m0 + fg) * ldp + ft;
+            const double* ahp = phs + (8 * m0 + fg) * ldp + ft;
+            for (int ks = 0; ks < kt; ++ks) {
+                const double b8v = __ldg(m8 + 4 * ks * ldb), bhv = __ldg(mh + 4 * ks * ldb);
+                const double s = is_es ? 1.0 : shape[4 * ks + ft];
+#pragma unroll
+                for (int c = 0; c < kMC; ++c)
+                    if (m0 + c < mt) {
+                        double a8v = a8p[c * 8 * ldp + 4 * ks], ahv = ahp[c * 8 * ldp + 4 * ks];
+                        if (!is_es) { a8v *= s; ahv *= s; }
+                        dmma_8x8x4(d8[c][0], d8[c][1], a8v, b8v);
+                        dmma_8x8x4(dh[c][0], dh[c][1], ahv, bhv);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < kMC; ++c)
+                if (m0 + c < mt) {
+                    const int row = 8 * (m0 + c) + fg;
+                    const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
+                    const double r0 = w * fma(f8, d8[c][0], fma(fh, dh[c][0], c0));
+                    const double r1 = w * fma(f8, d8[c][1], fma(fh, dh[c][1], c1));
+                    *reinterpret_cast<double2*>(rout + (size_t)row * ldr) = make_double2(r0, r1);
+                }
+        }
+    }
 }
 
 // The response fold is linear in the oscillation probabilities, so everything that does not depend on
@@ -425,50 +495,10 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
             }
         }
         __syncthreads();
-        // ---- fold on the FP64 tensor pipe: one (channel, 8-bin column block) per warp pass; kMC row tiles
-        //      stay in flight, so every k-step issues 2*kMC independent DMMAs behind two B-fragment loads -----
         const int ldr = 8 * max(nte, ntc);                  // row pitch of the folded-rate tiles
         double* rates_es = rbuf;
         double* rates_cc = rbuf + (size_t)8 * mt * ldr;
-        for (int task = warp; task < nte + ntc; task += kWarps) {
-            const bool is_es = task < nte;
-            if (is_es ? !D.es_mode : !D.cc_mode) continue;
-            const int n0 = 8 * (is_es ? task : task - nte);
-            const int ldb = 8 * (is_es ? nte : ntc);
-            const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
-            const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
-            const int j0 = n0 + 2 * ft;                                      // this lane's two columns
-            const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
-            double* rout = (is_es ? rates_es : rates_cc) + j0;
-            for (int m0 = 0; m0 < mt; m0 += kMC) {
-                double d8[kMC][2], dh[kMC][2];
-#pragma unroll
-                for (int c = 0; c < kMC; ++c) { d8[c][0] = d8[c][1] = dh[c][0] = dh[c][1] = 0.0; }
-                const double* a8p = p8s + (8 * m0 + fg) * ldp + ft;
-                const double* ahp = phs + (8 * m0 + fg) * ldp + ft;
-                for (int ks = 0; ks < kt; ++ks) {
-                    const double b8v = __ldg(m8 + 4 * ks * ldb), bhv = __ldg(mh + 4 * ks * ldb);
-                    const double s = is_es ? 1.0 : shape[4 * ks + ft];
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c)
-                        if (m0 + c < mt) {
-                            double a8v = a8p[c * 8 * ldp + 4 * ks], ahv = ahp[c * 8 * ldp + 4 * ks];
-                            if (!is_es) { a8v *= s; ahv *= s; }
-                            dmma_8x8x4(d8[c][0], d8[c][1], a8v, b8v);
-                            dmma_8x8x4(dh[c][0], dh[c][1], ahv, bhv);
-                        }
-                }
-#pragma unroll
-                for (int c = 0; c < kMC; ++c)
-                    if (m0 + c < mt) {
-                        const int row = 8 * (m0 + c) + fg;
-                        const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
-                        const double r0 = w * fma(f8, d8[c][0], fma(fh, dh[c][0], c0));
-                        const double r1 = w * fma(f8, d8[c][1], fma(fh, dh[c][1], c1));
-                        *reinterpret_cast<double2*>(rout + (size_t)row * ldr) = make_double2(r0, r1);
-                    }
-            }
-        }
+        fold_forward(T, D, f8, fh, p8s, phs, ldp, shape, cst_es, cst_cc, rates_es, rates_cc, ldr);
         __syncthreads();
         // ---- Poisson terms / outputs: the valid (row, reco bin) pairs are dealt out densely, two per
         //      thread per pass so that two logarithm chains overlap (likelihood_builder.jl:5-20,129-144) --
