@@ -62,6 +62,7 @@ struct solarosc_handle {
     std::vector<void*> dev_allocs;
     // per-detector data buffers (device, [1+n_cosz][n_ereco]) kept so set_data can overwrite them
     double *d_obs_es[kMaxDet]{}, *d_obs_cc[kMaxDet]{}, *d_log_es[kMaxDet]{}, *d_log_cc[kMaxDet]{};
+    double2 *d_ol_es[kMaxDet]{}, *d_ol_cc[kMaxDet]{};   // (m, log m) interleaved: one 16-byte load per Poisson term
     bool has_data[kMaxDet]{};
     // workspaces
     double* d_params2[2]{};      // double-buffered parameter chunks
@@ -75,6 +76,7 @@ struct solarosc_handle {
     size_t scratch_bytes = 0;
     size_t osc_smem_limit = 200 * 1024;
     size_t fused_smem = 0, seg_bytes = 0;
+    int fused_cb = 0, fused_grid = 0;    // coarse energy bins per oscillation chunk, CTAs of the persistent fused kernel
     bool fused_seg = false;
     bool rates_ok = true;
     bool fused_ok = false;
@@ -131,17 +133,21 @@ void upload_data(solarosc_handle* h, int d, const double* es_day, const double* 
                  const double* cc_night) {
     const int nZ = h->T.n_cosz;
     const bool cm = h->cfg.col_major != 0;
-    auto pack = [&](const double* day, const double* night, int nR, double* d_obs, double* d_log) {
-        std::vector<double> obs((size_t)(1 + nZ) * nR), lg(obs.size());
+    auto pack = [&](const double* day, const double* night, int nR, double* d_obs, double* d_log, double2* d_ol) {
+        std::vector<double> obs((size_t)(1 + nZ) * nR), lg(obs.size()), ol(2 * obs.size());
         std::copy(day, day + nR, obs.begin());
         std::vector<double> nt = to_row_major(night, nZ, nR, cm);
         std::copy(nt.begin(), nt.end(), obs.begin() + nR);
-        for (size_t i = 0; i < obs.size(); ++i) lg[i] = obs[i] > 0.0 ? std::log(obs[i]) : 0.0;
+        for (size_t i = 0; i < obs.size(); ++i) {
+            lg[i] = obs[i] > 0.0 ? std::log(obs[i]) : 0.0;
+            ol[2 * i] = obs[i]; ol[2 * i + 1] = lg[i];
+        }
         CK(cudaMemcpy(d_obs, obs.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_log, lg.data(), lg.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_ol, ol.data(), ol.size() * sizeof(double), cudaMemcpyHostToDevice));
     };
-    pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d]);
-    pack(cc_day, cc_night, h->n_cc[d], h->d_obs_cc[d], h->d_log_cc[d]);
+    pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d], h->d_ol_es[d]);
+    pack(cc_day, cc_night, h->n_cc[d], h->d_obs_cc[d], h->d_log_cc[d], h->d_ol_cc[d]);
     h->has_data[d] = true;
 }
 
@@ -281,7 +287,10 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         h->d_obs_cc[d] = h->dalloc<double>(nc); h->d_log_cc[d] = h->dalloc<double>(nc);
         CK(cudaMemset(h->d_obs_es[d], 0, ne * sizeof(double))); CK(cudaMemset(h->d_log_es[d], 0, ne * sizeof(double)));
         CK(cudaMemset(h->d_obs_cc[d], 0, nc * sizeof(double))); CK(cudaMemset(h->d_log_cc[d], 0, nc * sizeof(double)));
+        h->d_ol_es[d] = h->dalloc<double2>(ne); h->d_ol_cc[d] = h->dalloc<double2>(nc);
+        CK(cudaMemset(h->d_ol_es[d], 0, ne * sizeof(double2))); CK(cudaMemset(h->d_ol_cc[d], 0, nc * sizeof(double2)));
         D.obs_es = h->d_obs_es[d]; D.logobs_es = h->d_log_es[d]; D.obs_cc = h->d_obs_cc[d]; D.logobs_cc = h->d_log_cc[d];
+        D.ol_es = h->d_ol_es[d]; D.ol_cc = h->d_ol_cc[d];
         if (s.obs_es_day && s.obs_es_night && s.obs_cc_day && s.obs_cc_night)
             upload_data(h, d, s.obs_es_day, s.obs_es_night, s.obs_cc_day, s.obs_cc_night);
     }
@@ -309,16 +318,33 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(rates_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
-    // the fused kernel needs the whole energy axis of one point in one CTA
-    h->fused_smem = llh_smem_bytes(T.n_layers, T.n_etrue, T.n_cosz, h->max_ereco);
+    // Fused kernel: the energy axis is walked in chunks of fused_cb coarse bins, the smallest eigen table that
+    // still gives the propagation loop whole passes of work (n_cosz * cb items over kThreads threads), so that
+    // SOLAROSC_LLH_MINBLOCKS CTAs fit the SM's shared memory.  SOLAROSC_LLH_CHUNKS overrides the chunk count.
     h->seg_bytes = sizeof(double) * seg_smem_doubles(T.n_seg, T.n_paths, T.n_cosz);
-    // path tables ride along in shared memory while two CTAs still fit on an SM (or one, if two never did)
-    h->fused_seg = h->fused_smem + h->seg_bytes <= (h->fused_smem * 2 <= 220 * 1024 ? 110 * 1024 : prop.sharedMemPerBlockOptin);
-    if (h->fused_seg) h->fused_smem += h->seg_bytes;
-    h->fused_ok = h->fused_smem <= prop.sharedMemPerBlockOptin;
+    {
+        const size_t per_sm = prop.sharedMemPerMultiprocessor, per_cta_max = prop.sharedMemPerBlockOptin;
+        const size_t reserve = 1024;   // the driver keeps 1 kB per resident CTA
+        const size_t budget = std::min(per_cta_max, per_sm / SOLAROSC_LLH_MINBLOCKS - reserve);
+        int chunks = 1;
+        if (const char* e = std::getenv("SOLAROSC_LLH_CHUNKS")) chunks = std::max(1, atoi(e));
+        else
+            while (chunks < T.n_etrue &&
+                   llh_smem_bytes(T.n_layers, (T.n_etrue + chunks - 1) / chunks, T.n_etrue, T.n_cosz, h->max_ereco) + h->seg_bytes > budget)
+                ++chunks;
+        h->fused_cb = (T.n_etrue + chunks - 1) / chunks;
+        h->fused_smem = llh_smem_bytes(T.n_layers, h->fused_cb, T.n_etrue, T.n_cosz, h->max_ereco);
+        h->fused_seg = h->fused_smem + h->seg_bytes <= std::max(budget, h->fused_smem);
+        if (h->fused_seg) h->fused_smem += h->seg_bytes;
+        h->fused_ok = h->fused_smem <= per_cta_max;
+    }
     if (h->fused_ok) {
         CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         CK(cudaFuncSetAttribute(llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        // One CTA per oscillation point by default: measured 5 % faster than a persistent grid, whose CTAs march
+        // through their phases in lockstep and so never overlap one CTA's fold with the other's propagation.
+        h->fused_grid = 1 << 30;
+        if (const char* e = std::getenv("SOLAROSC_LLH_GRID")) h->fused_grid = std::max(1, atoi(e));
     }
 }
 
@@ -350,6 +376,7 @@ RatesLaunch rates_launch(solarosc_handle* h, int n, int group, int det_only) {
     RatesLaunch L{};
     L.n_points = n; L.group = group; L.param_stride = h->P; L.det_only = det_only; L.max_ereco = h->max_ereco;
     L.seg_smem = h->fused_seg ? 1 : 0;
+    L.osc_cb = h->fused_cb;
     const int d = det_only >= 0 ? det_only : 0;
     const bool cm = h->cfg.col_major != 0;
     L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? T.n_cosz : 1;
@@ -377,8 +404,9 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
     const int n_osc = n / group;
     if (h->fused_ok && h->use_fused && n_osc >= h->sm_count) {
         const RatesLaunch L = rates_launch(h, n, group, det_only);
-        if (mode == kModeLlh) llh_kernel<kModeLlh><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
-        else llh_kernel<kModeAsym><<<n_osc, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        const int grid = std::min(n_osc, h->fused_grid);
+        if (mode == kModeLlh) llh_kernel<kModeLlh><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        else llh_kernel<kModeAsym><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         CK(cudaGetLastError());
         ++h->launches;
         if (mid) CK(cudaEventRecord(mid, st));

@@ -31,6 +31,7 @@ struct DevDetector {
     int bg_cc_norm[SOLAROSC_MAX_BG];      // index of the CC nuisance scaling component i, -1 => fixed
     // data stored [1+n_cosz][n_ereco] (row 0 = day) and log(data) alongside
     const double *obs_es, *obs_cc, *logobs_es, *logobs_cc;
+    const double2 *ol_es, *ol_cc;         // (m, log m) interleaved, same indexing
 };
 
 struct DevTables {

@@ -26,9 +26,15 @@ namespace solarosc {
 #ifndef SOLAROSC_OSC_MINBLOCKS
 #define SOLAROSC_OSC_MINBLOCKS 2
 #endif
+#ifndef SOLAROSC_LLH_MINBLOCKS
+#define SOLAROSC_LLH_MINBLOCKS SOLAROSC_OSC_MINBLOCKS
+#endif
+#ifndef SOLAROSC_RATES_MINBLOCKS
+#define SOLAROSC_RATES_MINBLOCKS 2
+#endif
 constexpr int kThreads = SOLAROSC_OSC_THREADS;   // every kernel here uses this block size
 constexpr int kWarps = kThreads / 32;
-constexpr int kMC = 4;   // row tiles of the fold a warp keeps in flight
+constexpr int kMC = 7;   // row tiles of the fold a warp keeps in flight (51 rows = 7 tiles in the default binning)
 
 struct OscLaunch {
     int n_points;     // oscillation points in this launch
@@ -49,6 +55,7 @@ struct RatesLaunch {
     int det_only;      // -1: all detectors (likelihood), else the one detector whose arrays are written
     int max_ereco;     // largest reco-bin count of any detector/channel (sizes the shared-memory tiles)
     int seg_smem;      // fused kernel: path tables staged in shared memory behind the scratch
+    int osc_cb;        // fused kernel: coarse energy bins per oscillation chunk
     long long s_row_es, s_j_es, s_row_cc, s_j_cc;  // output strides of the night arrays (layout)
 };
 
@@ -76,23 +83,14 @@ __host__ __device__ inline int fold_ldp(int n_etrue) {
 __host__ __device__ inline int fold_rows(int nrow) { return 8 * ((nrow + 7) / 8); }
 __host__ __device__ inline size_t fold_p_doubles(int n_etrue, int nrow) { return (size_t)2 * fold_rows(nrow) * fold_ldp(n_etrue); }
 __host__ __device__ inline size_t fold_scratch_doubles(int n_etrue, int max_ereco) {
-    return (size_t)4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8) + 8;
-}
-// folded rates of both channels, [2][rows padded to 8][reco bins padded to 8]
-__host__ __device__ inline size_t fold_r_doubles(int nrow, int max_ereco) {
-    return (size_t)2 * fold_rows(nrow) * 8 * ((max_ereco + 7) / 8);
+    return (size_t)4 * 4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8) + 8;
 }
 __host__ __device__ inline size_t rates_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
-    return sizeof(double) * (fold_r_doubles(1 + n_cosz, max_ereco) + fold_p_doubles(n_etrue, 1 + n_cosz) +
-                             fold_scratch_doubles(n_etrue, max_ereco));
+    return sizeof(double) * (fold_p_doubles(n_etrue, 1 + n_cosz) + fold_scratch_doubles(n_etrue, max_ereco));
 }
-// in the fused kernel the folded-rate tiles reuse the eigen table's space, which is dead by then
-__host__ __device__ inline size_t llh_front_doubles(int n_layers, int n_etrue, int n_cosz, int max_ereco) {
-    const size_t a = osc_smem_doubles(n_layers, n_etrue), r = fold_r_doubles(1 + n_cosz, max_ereco);
-    return a > r ? a : r;
-}
-__host__ __device__ inline size_t llh_smem_bytes(int n_layers, int n_etrue, int n_cosz, int max_ereco) {
-    return sizeof(double) * (llh_front_doubles(n_layers, n_etrue, n_cosz, max_ereco) + fold_p_doubles(n_etrue, 1 + n_cosz) +
+// fused kernel: eigen table + MSW of one energy chunk (cb coarse bins), probability tile, scratch
+__host__ __device__ inline size_t llh_smem_bytes(int n_layers, int cb, int n_etrue, int n_cosz, int max_ereco) {
+    return sizeof(double) * (osc_smem_doubles(n_layers, cb) + fold_p_doubles(n_etrue, 1 + n_cosz) +
                              fold_scratch_doubles(n_etrue, max_ereco));
 }
 
@@ -325,15 +323,29 @@ __device__ __forceinline__ double log_pos(double x) {
     return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
 }
 
-// soft-floored Poisson term (reference likelihood_statistical.jl:16-24).  For raw_e - 1e-9 > 0.1 the
-// square root returns its argument's root exactly (the 1e-18 is below half an ulp of d^2), so the fast
-// branch is bit-identical to the formula.
+// Square root of a positive normal double (the soft floor's argument is >= 1e-18): reciprocal-square-root
+// seed, one coupled Newton step for sqrt and 1/(2 sqrt), one more for sqrt and a final residual correction.
+// Branch-free, so the Poisson terms a lane holds interleave; within 1 ulp.
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double g = x * r, h = 0.5 * r;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    return fma(fma(-g, g, x), h, g);
+}
+
+// soft-floored Poisson term (reference likelihood_statistical.jl:16-24), without branches: the logarithm is
+// taken of the floored expectation, which is positive whatever raw_e is.
 __device__ __forceinline__ double poisson_term(double raw_e, double m, double logm, uint32_t& fl) {
     if (raw_e < 0.0) fl |= (raw_e > -1e-3) ? SOLAROSC_FLAG_NEG_WARN : SOLAROSC_FLAG_NEG_ERROR;
     const double d = raw_e - 1e-9;
-    const double root = (d > 0.1) ? d : sqrt(fma(d, d, 1e-18));
-    const double e = 0.5 * (raw_e + 1e-9 + root);
-    return (m > 0.0) ? (e - m + m * (logm - log_pos(e))) : e;
+    const double e = 0.5 * (raw_e + 1e-9 + sqrt_pos(fma(d, d, 1e-18)));
+    const double t = e - m + m * (logm - log_pos(e));
+    return (m > 0.0) ? t : e;
 }
 
 // per-bin diagnostic term (reference likelihood_statistical.jl:31-57)
@@ -365,58 +377,6 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Forward fold on the FP64 tensor pipe: one (channel, 8-bin column block) per warp pass; kMC row tiles stay
-// in flight, so every k-step issues 2*kMC independent DMMAs behind two B-fragment loads.  Writes the
-// expected rates rates[row][j] = w_row (F8 G8 + Fh Gh + cst[j]) of both channels to shared memory.
-__device__ __forceinline__ void fold_forward(const DevTables& T, const DevDetector& D, double f8, double fh,
-                                             const double* p8s, const double* phs, int ldp, const double* shape,
-                                             const double* cst_es, const double* cst_cc, double* rates_es,
-                                             double* rates_cc, int ldr) {
-    const int nrow = 1 + T.n_cosz, kt = fold_kt(T.n_etrue), mt = (nrow + 7) / 8;
-    const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int fg = lane >> 2, ft = lane & 3;
-    for (int task = warp; task < nte + ntc; task += kWarps) {
-        const bool is_es = task < nte;
-        if (is_es ? !D.es_mode : !D.cc_mode) continue;
-        const int n0 = 8 * (is_es ? task : task - nte);
-        const int ldb = 8 * (is_es ? nte : ntc);
-        const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
-        const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
-        const int j0 = n0 + 2 * ft;                                      // this lane's two columns
-        const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
-        double* rout = (is_es ? rates_es : rates_cc) + j0;
-        for (int m0 = 0; m0 < mt; m0 += kMC) {
-            double d8[kMC][2], dh[kMC][2];
-#pragma unroll
-            for (int c = 0; c < kMC; ++c) { d8[c][0] = d8[c][1] = dh[c][0] = dh[c][1] = 0.0; }
-            const double* a8p = p8s + (8 * m0 + fg) * ldp + ft;
-            const double* ahp = phs + (8 * m0 + fg) * ldp + ft;
-            for (int ks = 0; ks < kt; ++ks) {
-                const double b8v = __ldg(m8 + 4 * ks * ldb), bhv = __ldg(mh + 4 * ks * ldb);
-                const double s = is_es ? 1.0 : shape[4 * ks + ft];
-#pragma unroll
-                for (int c = 0; c < kMC; ++c)
-                    if (m0 + c < mt) {
-                        double a8v = a8p[c * 8 * ldp + 4 * ks], ahv = ahp[c * 8 * ldp + 4 * ks];
-                        if (!is_es) { a8v *= s; ahv *= s; }
-                        dmma_8x8x4(d8[c][0], d8[c][1], a8v, b8v);
-                        dmma_8x8x4(dh[c][0], dh[c][1], ahv, bhv);
-                    }
-            }
-#pragma unroll
-            for (int c = 0; c < kMC; ++c)
-                if (m0 + c < mt) {
-                    const int row = 8 * (m0 + c) + fg;
-                    const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
-                    const double r0 = w * fma(f8, d8[c][0], fma(fh, dh[c][0], c0));
-                    const double r1 = w * fma(f8, d8[c][1], fma(fh, dh[c][1], c1));
-                    *reinterpret_cast<double2*>(rout + (size_t)row * ldr) = make_double2(r0, r1);
-                }
-        }
-    }
-}
-
 // The response fold is linear in the oscillation probabilities, so everything that does not depend on
 // the parameter point is folded into constant matrices at create time (host: build_fold_tables):
 //   ES[row][j] = w_row * ( F8 * sum_i P8[row][i] A8[i][j] + Fh * sum_i Ph[row][i] Ah[i][j] + cst_es[j] )
@@ -425,20 +385,34 @@ __device__ __forceinline__ void fold_forward(const DevTables& T, const DevDetect
 // cross-section shape, w_0 = 1 (day) and w_{1+z} the exposure weight, cst_es = F8 C8 + Fh Ch + BG_ES/2,
 // cst_cc = BG_CC/2 (reference propagation_osc.jl:159-210, propagation_core.jl:73-79,
 // propagation_reco.jl:10-29,117-130 rearranged; same arithmetic up to rounding order).
-// One warp owns one (channel, 8 reco bins) column block and sweeps the row tiles: per k-step it
-// loads two A fragments from shared memory, two B fragments through L1 and issues two DMMAs, so the
-// FP64 pipe, not the issue slots or the shared-memory port, limits the fold.
+//
+// The products run on the FP64 tensor pipe (DMMA m8n8k4).  One warp owns one (channel, 8 reco bins)
+// column block with all (up to kMC) row tiles in flight.  Flux and cross-section shape are applied to the
+// B fragment (one multiply per k-step and process instead of one per A element), both processes
+// accumulate into the same tile and the accumulators start from the additive constants, so per k-step a
+// warp issues 2 global loads (prefetched one step ahead), 2 + 2*kMC shared loads, 2 multiplies and 2*kMC
+// DMMAs.  The epilogue consumes the 8x8 output tiles straight from the accumulator registers -- Poisson
+// terms, asymmetry sums, or the rate / per-bin arrays -- so the folded rates never touch shared memory and
+// every lane carries 2*kMC independent logarithm chains.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 template <int MODE>
 __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
-                                           const double* p8s, const double* phs, int ldp, double* scr, double* rbuf,
+                                           const double* p8s, const double* phs, int ldp, double* scr,
                                            const RatesOut& O, double* red, uint32_t* redf) {
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fg = lane >> 2, ft = lane & 3;
     const double f8 = p[3], fh = p[4];
-    double* shape = scr;                     // [4*kt] CC cross-section shape, zero padded
-    double* cst_es = scr + 4 * kt;           // per reco bin additive constants
+    // scale vectors of the B fragments, [4*kt] each: ES 8B (F8), ES hep (Fh), CC 8B (F8 s_i), CC hep (Fh s_i)
+    double* scale = scr;
+    double* cst_es = scr + 16 * kt;          // per reco bin additive constants
     // earth-norm bounds (reference likelihood_debug.jl:1-4, likelihood_builder.jl:227)
     bool oob = false;
     if (T.earth_unc)
@@ -456,16 +430,17 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         double* cst_cc = cst_es + 8 * nte;
         double* bgs_es = cst_cc + 8 * ntc;       // summed backgrounds per reco bin (asymmetry mode)
         double* bgs_cc = bgs_es + 8 * nte;
-        __syncthreads();   // the previous point / detector is done with the scratch
+        __syncthreads();   // the previous point / detector is done with the scratch; orders the probability tile
         // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
         //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
         for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
-            double s = 0.0;
+            double sh = 0.0;
             if (i < nT) {
                 const double l = D.log_e_norm[i];
-                s = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
+                sh = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
             }
-            shape[i] = s;
+            scale[i] = f8; scale[4 * kt + i] = fh;
+            scale[8 * kt + i] = f8 * sh; scale[12 * kt + i] = fh * sh;
         }
         for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
             double acc = 0.0, c = 0.0;
@@ -475,7 +450,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                         const double raw = D.raw_bg_es[q * D.n_es + j];
                         acc += (D.bg_es_area[q] != 0.0) ? raw * (D.bg_es_area[q] * pd[0]) : raw;
                     }
-                    c = fma(f8, D.c8[j], fma(fh, D.ch[j], 0.5 * acc));
+                    c = fma(f8, D.c8[j], fma(fh, D.ch[j], 0.5 * acc));   // F8 C8 + Fh Ch + BG/2
                     if (MODE == kModeRates && O.bg_es) O.bg_es[b * D.n_es + j] = acc;
                 }
                 cst_es[j] = c;
@@ -494,87 +469,140 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                 if (MODE == kModeAsym) bgs_cc[jc] = acc;
             }
         }
+        // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
+        if (MODE == kModeRates || MODE == kModePerbin)
+            for (int ch = 0; ch < 2; ++ch) {
+                if (ch == 0 ? D.es_mode : D.cc_mode) continue;
+                const int nR = ch == 0 ? D.n_es : D.n_cc;
+                double* day = ch == 0 ? O.es_day : O.cc_day;
+                double* night = ch == 0 ? O.es_night : O.cc_night;
+                const double v = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
+                for (int o = threadIdx.x; o < nrow * nR; o += blockDim.x) {
+                    if (o < nR) { if (day) day[b * nR + o] = v; }
+                    else if (night) night[b * nZ * nR + (o - nR)] = v;
+                }
+            }
         __syncthreads();
-        const int ldr = 8 * max(nte, ntc);                  // row pitch of the folded-rate tiles
-        double* rates_es = rbuf;
-        double* rates_cc = rbuf + (size_t)8 * mt * ldr;
-        fold_forward(T, D, f8, fh, p8s, phs, ldp, shape, cst_es, cst_cc, rates_es, rates_cc, ldr);
-        __syncthreads();
-        // ---- Poisson terms / outputs: the valid (row, reco bin) pairs are dealt out densely, two per
-        //      thread per pass so that two logarithm chains overlap (likelihood_builder.jl:5-20,129-144) --
         double part = 0.0;
-        for (int ch = 0; ch < 2; ++ch) {
-            const bool is_es = ch == 0;
+        double d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;   // asymmetry mode: day / night totals above threshold
+        const uint32_t tile_bytes = 8u * (uint32_t)ldp * 8u;   // one 8-row tile of the probability tile
+        for (int task = warp; task < nte + ntc; task += kWarps) {
+            const bool is_es = task < nte;
+            if (is_es ? !D.es_mode : !D.cc_mode) continue;
+            const int n0 = 8 * (is_es ? task : task - nte);
+            const int ldb = 8 * (is_es ? nte : ntc);
             const int nR = is_es ? D.n_es : D.n_cc;
+            const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
+            const int j0 = n0 + 2 * ft;                                      // this lane's two columns
+            // likelihood and asymmetry only look at the bins from the threshold on (likelihood_builder.jl:5-20,129-144)
+            const int jlo = (MODE == kModeLlh || MODE == kModeAsym) ? idx0 : 0;
+            if ((MODE == kModeLlh || MODE == kModeAsym) && n0 + 8 <= jlo) continue;   // column block below threshold
+            const bool v0 = j0 >= jlo && j0 < nR, v1 = j0 + 1 >= jlo && j0 + 1 < nR;
+            const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
+            const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
+            const uint32_t sc8 = smem_addr(scale + (is_es ? 0 : 8 * kt) + ft), sch = sc8 + 4u * kt * 8u;
+            const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
+            const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
+            const double* obs = is_es ? D.obs_es : D.obs_cc;
             double* day = is_es ? O.es_day : O.cc_day;
             double* night = is_es ? O.es_night : O.cc_night;
             const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
-            if (is_es ? !D.es_mode : !D.cc_mode) {
-                if (MODE == kModeAsym) {
-                    double* out = is_es ? O.asym_es : O.asym_cc;
-                    if (out && threadIdx.x == 0) out[b] = 0.0;
-                } else if (MODE != kModeLlh) {   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
-                    const double v = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
-                    for (int o = threadIdx.x; o < nrow * nR; o += blockDim.x) {
-                        if (o < nR) { if (day) day[b * nR + o] = v; }
-                        else if (night) night[b * nZ * nR + (o - nR)] = v;
+            const size_t bstep = (size_t)4 * ldb;
+            for (int m0 = 0; m0 < mt; m0 += kMC) {
+                double acc[kMC][2];
+                uint32_t a8[kMC];   // shared-memory address of this lane's A element of k-step 0, per row tile
+#pragma unroll
+                for (int c = 0; c < kMC; ++c) {
+                    acc[c][0] = c0; acc[c][1] = c1;
+                    // tiles past the end repeat the last one: their results are dropped in the epilogue
+                    a8[c] = smem_addr(p8s + fg * ldp + ft) + (uint32_t)min(m0 + c, mt - 1) * tile_bytes;
+                }
+                const uint32_t dproc = smem_addr(phs) - smem_addr(p8s);
+                double b8n = __ldg(m8), bhn = __ldg(mh);
+                const double *q8 = m8, *qh = mh;
+                for (int ks = 0; ks < kt; ++ks) {
+                    const double b8v = b8n * lds_f64(sc8 + 32u * ks), bhv = bhn * lds_f64(sch + 32u * ks);
+                    if (ks + 1 < kt) { q8 += bstep; qh += bstep; b8n = __ldg(q8); bhn = __ldg(qh); }
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) {
+                        dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + 32u * ks), b8v);
+                        dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + dproc + 32u * ks), bhv);
                     }
                 }
-                continue;
-            }
-            const double* rin = is_es ? rates_es : rates_cc;
-            const double* obs = is_es ? D.obs_es : D.obs_cc;
-            const double* lobs = is_es ? D.logobs_es : D.logobs_cc;
-            const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
-            // likelihood mode only visits the bins above threshold: nc columns from jlo
-            const int jlo = (MODE == kModeLlh || MODE == kModeAsym) ? idx0 : 0, nc = nR - jlo;
-            double dsum = 0.0, nsum = 0.0;          // asymmetry mode: day / night totals above threshold
-            const int dq = (int)blockDim.x / nc, dr = (int)blockDim.x - dq * nc;
-            int row = (int)threadIdx.x / nc, jj = (int)threadIdx.x - row * nc;
-            while (row < nrow) {
-                int row2 = row + dq, jj2 = jj + dr;          // the element one pass further on
-                if (jj2 >= nc) { jj2 -= nc; ++row2; }
-                const bool two = row2 < nrow;
-                const int j = jlo + jj, od = row * nR + j;
-                const int jb = jlo + jj2, od2 = two ? row2 * nR + jb : od;
-                const double rate = rin[row * ldr + j], rate2 = rin[(two ? row2 : row) * ldr + (two ? jb : j)];
+                // ---- epilogue on the accumulator registers ----------------------------------------------
+                double r[kMC][2];
+                bool vr[kMC];
+#pragma unroll
+                for (int c = 0; c < kMC; ++c) {
+                    const int row = 8 * (m0 + c) + fg;
+                    vr[c] = m0 + c < mt && row < nrow;
+                    const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
+                    r[c][0] = w * acc[c][0];
+                    r[c][1] = w * acc[c][1];
+                }
                 if (MODE == kModeLlh) {
-                    const double t1 = poisson_term(rate, obs[od], lobs[od], fl);
-                    const double t2 = poisson_term(rate2, obs[od2], lobs[od2], fl);
-                    part += two ? t1 + t2 : t1;
+                    double2 o0[kMC], o1[kMC];
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) {
+                        const int row = 8 * (m0 + c) + fg;
+                        o0[c] = (vr[c] && v0) ? __ldg(ol + row * nR + j0) : make_double2(0.0, 0.0);
+                        o1[c] = (vr[c] && v1) ? __ldg(ol + row * nR + j0 + 1) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) {
+                        const double t0 = poisson_term((vr[c] && v0) ? r[c][0] : 1.0, o0[c].x, o0[c].y, fl);
+                        const double t1 = poisson_term((vr[c] && v1) ? r[c][1] : 1.0, o1[c].x, o1[c].y, fl);
+                        part += ((vr[c] && v0) ? t0 : 0.0) + ((vr[c] && v1) ? t1 : 0.0);
+                    }
                 } else if (MODE == kModeAsym) {
-                    if (row == 0) dsum += rate; else nsum += rate;
-                    if (two) { if (row2 == 0) dsum += rate2; else nsum += rate2; }
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) {
+                        const double s01 = ((vr[c] && v0) ? r[c][0] : 0.0) + ((vr[c] && v1) ? r[c][1] : 0.0);
+                        const bool is_day = m0 + c == 0 && fg == 0;
+                        if (is_es) { if (is_day) d_es += s01; else n_es += s01; }
+                        else { if (is_day) d_cc += s01; else n_cc += s01; }
+                    }
                 } else {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !two) break;
-                        const int rr = h ? row2 : row, jx = h ? jb : j, oo = h ? od2 : od;
-                        double v = h ? rate2 : rate;
-                        if (MODE == kModePerbin) {
-                            v = (jx >= idx0 && jx < nR - 1) ? perbin_term(v, obs[oo]) : 0.0;
-                            if (oob) v = -INFINITY;
-                        }
-                        if (rr == 0) {
-                            if (day) day[b * nR + jx] = v;
-                        } else if (night) {
-                            night[b * nZ * nR + (size_t)(rr - 1) * sr + (size_t)jx * sj] = v;
+                    for (int c = 0; c < kMC; ++c) {
+                        if (!vr[c]) continue;
+                        const int row = 8 * (m0 + c) + fg;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int jx = j0 + h;
+                            if (jx >= nR) continue;
+                            double v = r[c][h];
+                            if (MODE == kModePerbin) {
+                                v = (jx >= idx0 && jx < nR - 1) ? perbin_term(v, obs[row * nR + jx]) : 0.0;
+                                if (oob) v = -INFINITY;
+                            }
+                            if (row == 0) {
+                                if (day) day[b * nR + jx] = v;
+                            } else if (night) {
+                                night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = v;
+                            }
                         }
                     }
                 }
-                jj = jj2 + dr; row = row2 + dq;
-                if (jj >= nc) { jj -= nc; ++row; }
             }
-            if (MODE == kModeAsym) {
-                // derive_variables_from_chain.jl:236-258: half of the background above threshold is taken off
-                // the day total and half off the night total; a zero denominator gives 0
-                const double dtot = block_sum(dsum, red), ntot = block_sum(nsum, red);
+        }
+        if (MODE == kModeAsym) {
+            // derive_variables_from_chain.jl:236-258: half of the background above threshold is taken off
+            // the day total and half off the night total; a zero denominator gives 0
+            for (int ch = 0; ch < 2; ++ch) {
+                const bool is_es = ch == 0;
+                double* out = is_es ? O.asym_es : O.asym_cc;
+                if (is_es ? !D.es_mode : !D.cc_mode) {
+                    if (out && threadIdx.x == 0) out[b] = 0.0;
+                    continue;
+                }
+                const double dtot = block_sum(is_es ? d_es : d_cc, red), ntot = block_sum(is_es ? n_es : n_cc, red);
                 if (threadIdx.x == 0) {
                     const double* bgs = is_es ? bgs_es : bgs_cc;
+                    const int nR = is_es ? D.n_es : D.n_cc, idx0 = (is_es ? D.index_es : D.index_cc) - 1;
                     double bg = 0.0;
                     for (int j = idx0; j < nR; ++j) bg += bgs[j];
                     const double dd = dtot - 0.5 * bg, nn = ntot - 0.5 * bg, den = dd + nn;
-                    double* out = is_es ? O.asym_es : O.asym_cc;
                     if (out) out[b] = (den == 0.0) ? 0.0 : 2.0 * (dd - nn) / den;
                 }
             }
@@ -600,27 +628,27 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
     }
 }
 
-// zero the padding of the shared-memory probability tile (rows >= nrow, columns >= n_etrue) of both processes
+// Zero the K padding of the probability tile (columns n_etrue .. 4*ceil(n_etrue/4) - 1 of both processes): the fold
+// multiplies them by the zero rows of the constant matrices, so they must be finite.  Padding ROWS need nothing:
+// an output row of an MMA only depends on the same row of A, and the epilogue drops rows >= nrow.
 __device__ __forceinline__ void fold_zero_padding(double* ps, int nT, int nrow, int ldp) {
-    const int rows = fold_rows(nrow), padc = ldp - nT;
-    for (int proc = 0; proc < 2; ++proc) {
-        double* q = ps + (size_t)proc * rows * ldp;
-        for (int t = threadIdx.x; t < (rows - nrow) * ldp; t += blockDim.x) q[nrow * ldp + t] = 0.0;
-        for (int r = threadIdx.x; r < nrow; r += blockDim.x)
-            for (int c = 0; c < padc; ++c) q[r * ldp + nT + c] = 0.0;
+    const int rows = fold_rows(nrow), padc = 4 * fold_kt(nT) - nT;
+    if (padc == 0) return;
+    for (int t = threadIdx.x; t < 2 * rows * padc; t += blockDim.x) {
+        const int r = t / padc, c = t - r * padc;
+        ps[(size_t)r * ldp + nT + c] = 0.0;
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SOLAROSC_RATES_MINBLOCKS)
 rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params,
              const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
     extern __shared__ double smem[];
     __shared__ double red[kWarps];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
-    double* rbuf = smem;
-    double* p8s = smem + fold_r_doubles(nrow, L.max_ereco);
+    double* p8s = smem;
     double* phs = p8s + (size_t)rows * ldp;
     double* scr = p8s + fold_p_doubles(nT, nrow);
     const size_t b = blockIdx.x;
@@ -636,31 +664,42 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
             if (i >= nT) { i -= nT; ++row; }
         }
     }
-    fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, rbuf, O, red, redf);
+    fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf);
 }
 
-// One CTA per oscillation point: K1+K2 into shared memory, then K3+K4+K5 for each of the `group`
-// parameter points sharing it.
+// Persistent fused kernel: every CTA walks oscillation points g = blockIdx.x, blockIdx.x + gridDim.x, ...  Per
+// point: K1+K2 into the shared-memory probability tile, one energy chunk (L.osc_cb coarse bins) at a time so
+// that the eigen table stays small enough for several CTAs per SM, then K3+K4+K5 for each of the `group`
+// parameter points sharing it.  The oscillation probabilities never leave the SM.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SOLAROSC_LLH_MINBLOCKS)
 llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params, RatesOut O) {
     extern __shared__ double smem[];
     __shared__ double red[kWarps];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    const int cbs = L.osc_cb;
     double* tbl = smem;
-    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * nT;
-    double* p8s = smem + llh_front_doubles(T.n_layers, nT, T.n_cosz, L.max_ereco);
+    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * cbs;
+    double* p8s = smem + osc_smem_doubles(T.n_layers, cbs);
     double* phs = p8s + (size_t)rows * ldp;
     double* scr = p8s + fold_p_doubles(nT, nrow);
-    const size_t g = blockIdx.x;
     const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), L.seg_smem != 0);
     fold_zero_padding(p8s, nT, nrow, ldp);
-    osc_stage(T, G, params + g * L.group * L.param_stride, 0, nT, nT, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
-    for (int q = 0; q < L.group; ++q) {
-        const size_t b = g * L.group + q;
-        // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
-        fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, smem, O, red, redf);
+    const int n_osc = L.n_points / L.group;
+    for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
+        const double* po = params + (size_t)g * L.group * L.param_stride;
+        for (int i0 = 0; i0 < nT; i0 += cbs) {
+            // the table of the previous chunk is still being read by slower warps; the previous point's fold is
+            // done with the probability tile once its closing barrier has been passed
+            if (i0 > 0) __syncthreads();
+            osc_stage(T, G, po, i0, min(cbs, nT - i0), cbs, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
+        }
+        for (int q = 0; q < L.group; ++q) {
+            const size_t b = (size_t)g * L.group + q;
+            // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
+            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf);
+        }
     }
 }
 
