@@ -190,7 +190,6 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     REQUIRE(t->seg_start[0] == 0 && n_seg > 0, "seg_start must start at 0");
     T.n_seg = n_seg;
     T.e_calc = h->upload(t->e_calc, T.n_e);
-    T.path_start = h->upload(t->seg_start, T.n_paths + 1);
     // Applied order of the steps of each path (reference osc.jl:436-446 and :455-456): step m uses
     // layer index[n-1-m] paired with length[m] of the stored detector->surface segment list.
     std::vector<int> app_layer(n_seg);
@@ -207,12 +206,20 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         }
         row_cost[pth / T.n_sub] += n;
     }
-    T.app_layer = h->upload(app_layer.data(), n_seg);
-    T.app_len = h->upload(app_len.data(), n_seg);
+    std::vector<Seg> seg(n_seg);
+    for (int i = 0; i < n_seg; ++i) seg[i] = Seg{app_len[i], app_layer[i], 0};
+    T.seg = h->upload(seg.data(), n_seg);
     std::vector<int> order(T.n_cosz);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_cost[a] > row_cost[b]; });
     T.row_order = h->upload(order.data(), T.n_cosz);
+    std::vector<int2> se(T.n_paths);
+    for (int zr = 0; zr < T.n_cosz; ++zr)
+        for (int sub = 0; sub < T.n_sub; ++sub) {
+            const int pth = order[zr] * T.n_sub + sub;
+            se[zr * T.n_sub + sub] = make_int2(t->seg_start[pth], t->seg_start[pth + 1]);
+        }
+    T.path_se = h->upload(se.data(), T.n_paths);
     T.earth_lookup = h->upload(t->earth_lookup, T.n_layers);
     T.wz = h->upload(t->exposure_weights, T.n_cosz);
     T.avg_ne[0] = t->avg_ne_8b; T.avg_ne[1] = t->avg_ne_hep;
@@ -267,6 +274,18 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
             }
             D.a8 = h->upload_vec(a8); D.ah = h->upload_vec(ah); D.c8 = h->upload_vec(c8); D.ch = h->upload_vec(chh);
             D.b8 = h->upload_vec(b8); D.bh = h->upload_vec(bh);
+            // copies that start at the threshold bin (likelihood / asymmetry modes)
+            auto shifted = [&](const std::vector<double>& m, int ld, int nR, int idx0, int& blocks) {
+                blocks = (nR - idx0 + 7) / 8;
+                std::vector<double> out((size_t)kp * 8 * blocks, 0.0);
+                for (int i = 0; i < nT; ++i)
+                    for (int j = idx0; j < nR; ++j) out[(size_t)i * 8 * blocks + (j - idx0)] = m[(size_t)i * ld + j];
+                return out;
+            };
+            D.a8_thr = h->upload_vec(shifted(a8, le, D.n_es, D.index_es - 1, D.nte_thr));
+            D.ah_thr = h->upload_vec(shifted(ah, le, D.n_es, D.index_es - 1, D.nte_thr));
+            D.b8_thr = h->upload_vec(shifted(b8, lc, D.n_cc, D.index_cc - 1, D.ntc_thr));
+            D.bh_thr = h->upload_vec(shifted(bh, lc, D.n_cc, D.index_cc - 1, D.ntc_thr));
         }
         D.raw_bg_es = h->upload(s.raw_bg_es, (size_t)D.n_bg_es * D.n_es);
         D.raw_bg_cc = h->upload(s.raw_bg_cc, (size_t)D.n_bg_cc * D.n_cc);

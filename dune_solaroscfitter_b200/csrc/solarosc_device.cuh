@@ -19,6 +19,12 @@ constexpr double kPhase = 2.5338653580781976;     // reference osc.jl:361
 constexpr double kDm31 = 2.5e-3;                  // reference osc.jl:44 (theta23, deltaCP drop out of P1e)
 constexpr int kMaxDet = 4;
 
+// one applied layer step: 0-based layer and length [km]; 16 bytes so a step's metadata is one load
+struct __align__(16) Seg {
+    double len;
+    int layer, pad;
+};
+
 struct DevDetector {
     int es_mode, cc_mode, n_es, n_cc, index_es, index_cc, n_bg_es, n_bg_cc, n_norm_es, n_norm_cc, param_off;
     const double* log_e_norm;             // [n_etrue]
@@ -26,6 +32,9 @@ struct DevDetector {
     const double *a8, *ah;                // ES, 8B / hep
     const double *b8, *bh;                // CC, 8B / hep (without the per-point cross-section shape)
     const double *c8, *ch;                // ES additive constants per reco bin, [8*ceil(n_es/8)]
+    // the same matrices with the columns below the likelihood threshold removed: column j' is reco bin index_xx - 1 + j'
+    const double *a8_thr, *ah_thr, *b8_thr, *bh_thr;
+    int nte_thr, ntc_thr;                 // their widths in 8-column blocks
     const double *raw_bg_es, *raw_bg_cc;  // [n_bg][n_ereco]
     double bg_es_area[SOLAROSC_MAX_BG];   // face area per ES component (0 => not scaled by a nuisance)
     int bg_cc_norm[SOLAROSC_MAX_BG];      // index of the CC nuisance scaling component i, -1 => fixed
@@ -38,10 +47,9 @@ struct DevTables {
     int n_etrue, n_e, n_cosz, n_sub, n_paths, n_layers, n_solar, n_seg, n_det, n_params;
     int fast, earth_unc;
     const double* e_calc;      // [n_e]
-    const int* path_start;     // [n_paths+1]
-    const int* app_layer;      // [n_seg] 0-based layer of the m-th APPLIED step of each path
-    const double* app_len;     // [n_seg] its length [km]
-    const int* row_order;      // [n_cosz] coarse zenith rows, longest paths first
+    const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path
+    const int2* path_se;       // [n_cosz*n_sub] (first, one-past-last) step of the paths of sorted row zr, sub-path fastest
+    const int* row_order;      // [n_cosz] coarse zenith bin of sorted row zr (longest paths first)
     const double* earth_lookup;// [n_layers]
     const double* wz;          // [n_cosz]
     double avg_ne[2];

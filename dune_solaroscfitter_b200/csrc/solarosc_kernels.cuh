@@ -123,29 +123,27 @@ struct SmemSink {
 };
 
 // Path tables as the propagation loop reads them: in shared memory when they fit (every layer step
-// needs its layer id and length, and a global load there sits on the critical path), else in HBM.
+// needs its layer id and length), else in HBM.  Rows are listed longest path first.
 struct SegTables {
-    const int* path_start;
-    const int* app_layer;
-    const double* app_len;
-    const int* row_order;
+    const Seg* seg;         // [n_seg] applied steps of all paths
+    const int2* path_se;    // [n_cosz * n_sub] (first, one-past-last) step of the paths of sorted row zr
+    const int* row_order;   // [n_cosz] zenith bin of sorted row zr
 };
 
 __host__ __device__ inline size_t seg_smem_doubles(int n_seg, int n_paths, int n_cosz) {
-    return (size_t)n_seg + ((size_t)n_seg + n_paths + 1 + n_cosz + 1) / 2 + 1;
+    return (size_t)2 * n_seg + n_paths + ((size_t)n_cosz + 1) / 2 + 1;
 }
 
-// Copies the path tables behind `buf` (no barrier: the caller's next __syncthreads orders it).
+// Copies the path tables behind `buf` (16-byte aligned; no barrier: the caller's next __syncthreads orders it).
 __device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double* buf, bool to_smem) {
-    if (!to_smem) return SegTables{T.path_start, T.app_layer, T.app_len, T.row_order};
-    double* len = buf;
-    int* lay = reinterpret_cast<int*>(buf + T.n_seg);
-    int* start = lay + T.n_seg;
-    int* order = start + T.n_paths + 1;
-    for (int t = threadIdx.x; t < T.n_seg; t += blockDim.x) { len[t] = T.app_len[t]; lay[t] = T.app_layer[t]; }
-    for (int t = threadIdx.x; t <= T.n_paths; t += blockDim.x) start[t] = T.path_start[t];
+    if (!to_smem) return SegTables{T.seg, T.path_se, T.row_order};
+    Seg* seg = reinterpret_cast<Seg*>(buf);
+    int2* se = reinterpret_cast<int2*>(buf + 2 * T.n_seg);
+    int* order = reinterpret_cast<int*>(buf + 2 * T.n_seg + T.n_paths);
+    for (int t = threadIdx.x; t < T.n_seg; t += blockDim.x) seg[t] = T.seg[t];
+    for (int t = threadIdx.x; t < T.n_paths; t += blockDim.x) se[t] = T.path_se[t];
     for (int t = threadIdx.x; t < T.n_cosz; t += blockDim.x) order[t] = T.row_order[t];
-    return SegTables{start, lay, len, order};
+    return SegTables{seg, se, order};
 }
 
 template <class Sink>
@@ -210,26 +208,31 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
                  0.5 * (msw[(size_t)2 * 2 * cbs + j] + msw[(size_t)2 * 2 * cbs + cbs + j]));
 
     // ---- phase 2: Earth propagation, one item = (coarse zenith row, coarse energy bin) -----------
-    // Lanes of a warp walk the same path at neighbouring energies, so the layer loop is
-    // warp-uniform; rows are visited longest-first so the tail of the item loop is the cheap rows.
+    // Lanes of a warp walk the same path at neighbouring energies, so the layer loop is warp-uniform.
+    // Rows are visited longest-first and the passes alternate direction (thread t takes item t of even
+    // passes and item nthreads-1-t of odd ones), so every thread gets the same mix of long and short paths.
     const double inv_block = 1.0 / (2.0 * T.n_sub);
     const int n_items = T.n_cosz * cb;
-    for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
-        const int zr = item / cb, j = item - zr * cb;
-        const int z = G.row_order[zr];
+    const double inv_cb = 1.0 / cb;
+    const int ls = 2 * cbs * kEntry;                            // doubles between consecutive layers
+    for (int base = 0, pass = 0; base < n_items; base += blockDim.x, ++pass) {
+        const int item = base + ((pass & 1) ? (int)blockDim.x - 1 - (int)threadIdx.x : (int)threadIdx.x);
+        if (item >= n_items) continue;
+        const int zr = (int)((item + 0.5) * inv_cb), j = item - zr * cb;   // exact: item < 2^31, cb >= 1
         double acc8 = 0.0, acch = 0.0;
         const double* t0 = tbl + (size_t)j * kEntry;           // even fine energy of this coarse bin, layer 0
         const double* t1 = t0 + (size_t)cbs * kEntry;          // odd fine energy
-        const int ls = 2 * cbs * kEntry;                        // doubles between consecutive layers
         for (int sub = 0; sub < T.n_sub; ++sub) {
-            const int path = z * T.n_sub + sub;
-            const int s0 = G.path_start[path], s1 = G.path_start[path + 1];
+            const int2 se = G.path_se[zr * T.n_sub + sub];
+            const int s0 = se.x, s1 = se.y;
             // Both fine energies of the bin advance through the layers together: two independent
             // dependency chains per thread keep the FP64 pipe fed (osc_reduce_from_lookup, osc.jl:436-446).
+            // The (layer, length) of the next step is fetched while the current one is computed.
             State pa, pb;
             {
-                const int k = G.app_layer[s0] * ls;
-                const double len = G.app_len[s0];
+                Seg sg = G.seg[s0];
+                const int k = sg.layer * ls;
+                const double len = sg.len;
                 if (s1 - s0 == 1) {
                     double y1r, y1i, y2r, y2i;
                     step_phases(t0 + k, len, y1r, y1i, y2r, y2i);
@@ -239,24 +242,25 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
                     pb.ar = fma(t1[k + 3], y2r * t1[k + 9], fma(t1[k], y1r * t1[k + 8], u1));
                     pb.ai = fma(t1[k + 3], y2i * t1[k + 9], t1[k] * (y1i * t1[k + 8]));
                 } else {
+                    sg = G.seg[s0 + 1];
                     step_first(t0 + k, len, u1, u2, u3, pa);
                     step_first(t1 + k, len, u1, u2, u3, pb);
                     for (int s = s0 + 1; s < s1 - 1; ++s) {
-                        const int km = G.app_layer[s] * ls;
-                        const double lm = G.app_len[s];
+                        const int km = sg.layer * ls;
+                        const double lm = sg.len;
+                        sg = G.seg[s + 1];
                         step_mid(t0 + km, lm, pa);
                         step_mid(t1 + km, lm, pb);
                     }
-                    const int kl = G.app_layer[s1 - 1] * ls;
-                    const double ll = G.app_len[s1 - 1];
-                    step_last(t0 + kl, ll, pa);
-                    step_last(t1 + kl, ll, pb);
+                    const int kl = sg.layer * ls;
+                    step_last(t0 + kl, sg.len, pa);
+                    step_last(t1 + kl, sg.len, pb);
                 }
             }
             const double pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);   // |<nu_1|X|nu_e>|^2 (osc.jl:444)
             const double pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
             if (p1e_out) {
-                double* o = p1e_out + (size_t)path * T.n_e + 2 * (i0 + j);
+                double* o = p1e_out + (size_t)(G.row_order[zr] * T.n_sub + sub) * T.n_e + 2 * (i0 + j);
                 o[0] = pe0; o[1] = pe1;
             }
             // IYSW night probability (osc.jl:204): P_day + c13^2 cos2theta_m (P1e - P0)
@@ -265,7 +269,7 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
             acch += fma(msw[(size_t)3 * 2 * cbs + j], d0, msw[(size_t)2 * 2 * cbs + j]) +
                     fma(msw[(size_t)3 * 2 * cbs + cbs + j], d1, msw[(size_t)2 * 2 * cbs + cbs + j]);
         }
-        sink.put(1 + z, i0 + j, acc8 * inv_block, acch * inv_block);   // block_average (propagation_osc.jl:136-137)
+        sink.put(1 + G.row_order[zr], i0 + j, acc8 * inv_block, acch * inv_block);   // block_average (propagation_osc.jl:136-137)
     }
 }
 
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, SOLAROSC_OSC_MINBLOCKS)
 osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ params,
            double* __restrict__ osc_out /* [n_points][2][1+n_cosz][n_etrue] */,
            double* __restrict__ p1e_out /* [n_points][n_paths][n_e] or nullptr */) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int g = blockIdx.x / L.n_chunks;               // output slot: (point, variant)
     const int chunk = blockIdx.x - g * L.n_chunks;
     const int point = g / L.n_var, var = g - point * L.n_var;
@@ -486,22 +490,24 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         double part = 0.0;
         double d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;   // asymmetry mode: day / night totals above threshold
         const uint32_t tile_bytes = 8u * (uint32_t)ldp * 8u;   // one 8-row tile of the probability tile
-        for (int task = warp; task < nte + ntc; task += kWarps) {
-            const bool is_es = task < nte;
+        // likelihood and asymmetry only look at the bins from the threshold on (likelihood_builder.jl:5-20,129-144):
+        // they use the copies of the fold matrices whose columns start at the threshold bin, so no column block is
+        // spent on bins that never enter the sum (24 bins = 3 blocks instead of 4 per channel in the default binning)
+        constexpr bool kThr = MODE == kModeLlh || MODE == kModeAsym;
+        const int bte = kThr ? D.nte_thr : nte, btc = kThr ? D.ntc_thr : ntc;
+        for (int task = warp; task < bte + btc; task += kWarps) {
+            const bool is_es = task < bte;
             if (is_es ? !D.es_mode : !D.cc_mode) continue;
-            const int n0 = 8 * (is_es ? task : task - nte);
-            const int ldb = 8 * (is_es ? nte : ntc);
+            const int n0 = 8 * (is_es ? task : task - bte);
+            const int ldb = 8 * (is_es ? bte : btc);
             const int nR = is_es ? D.n_es : D.n_cc;
             const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
-            const int j0 = n0 + 2 * ft;                                      // this lane's two columns
-            // likelihood and asymmetry only look at the bins from the threshold on (likelihood_builder.jl:5-20,129-144)
-            const int jlo = (MODE == kModeLlh || MODE == kModeAsym) ? idx0 : 0;
-            if ((MODE == kModeLlh || MODE == kModeAsym) && n0 + 8 <= jlo) continue;   // column block below threshold
-            const bool v0 = j0 >= jlo && j0 < nR, v1 = j0 + 1 >= jlo && j0 + 1 < nR;
-            const double* m8 = (is_es ? D.a8 : D.b8) + ft * ldb + n0 + fg;   // B fragment of k-step 0
-            const double* mh = (is_es ? D.ah : D.bh) + ft * ldb + n0 + fg;
+            const int j0 = (kThr ? idx0 : 0) + n0 + 2 * ft;                  // this lane's two reco bins
+            const bool v0 = j0 < nR, v1 = j0 + 1 < nR;
+            const double* m8 = (kThr ? (is_es ? D.a8_thr : D.b8_thr) : (is_es ? D.a8 : D.b8)) + ft * ldb + n0 + fg;   // B fragment of k-step 0
+            const double* mh = (kThr ? (is_es ? D.ah_thr : D.bh_thr) : (is_es ? D.ah : D.bh)) + ft * ldb + n0 + fg;
             const uint32_t sc8 = smem_addr(scale + (is_es ? 0 : 8 * kt) + ft), sch = sc8 + 4u * kt * 8u;
-            const double c0 = (is_es ? cst_es : cst_cc)[j0], c1 = (is_es ? cst_es : cst_cc)[j0 + 1];
+            const double c0 = v0 ? (is_es ? cst_es : cst_cc)[j0] : 0.0, c1 = v1 ? (is_es ? cst_es : cst_cc)[j0 + 1] : 0.0;
             const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
             const double* obs = is_es ? D.obs_es : D.obs_cc;
             double* day = is_es ? O.es_day : O.cc_day;
@@ -644,7 +650,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, SOLAROSC_RATES_MINBLOCKS)
 rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params,
              const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ double red[kWarps];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
@@ -674,7 +680,7 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, SOLAROSC_LLH_MINBLOCKS)
 llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params, RatesOut O) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ double red[kWarps];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
