@@ -812,6 +812,15 @@ int solarosc_last_timing(solarosc_handle* h, float* ms_osc, float* ms_rates) {
 
 int solarosc_last_fused(const solarosc_handle* h) { return h ? (h->last_fused ? 1 : 0) : -1; }
 
+#ifdef SOLAROSC_PHASE_TIMING
+// diagnostic builds only: clock64 stamps of CTAs kPhaseFirst .. kPhaseFirst + kPhaseCtas - 1 of the last fused launch
+int solarosc_debug_read_phases(long long* out, int* n_slots, int* n_ctas) {
+    cudaDeviceSynchronize();
+    *n_slots = kPhaseSlots; *n_ctas = kPhaseCtas;
+    return cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * kPhaseSlots * kPhaseCtas) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 int solarosc_measure_fp64_peak(solarosc_handle* h, double* tflops) {
     return guarded(h, [&]() {
         REQUIRE(tflops, "NULL pointer");

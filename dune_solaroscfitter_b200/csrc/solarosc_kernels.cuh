@@ -46,6 +46,20 @@ struct OscLaunch {
     int n_var;        // 1, or 1 + 2*n_dir: every point is followed by its +/- finite-difference variants
 };
 
+// Phase timestamps of a window of CTAs (diagnostic builds only: -DSOLAROSC_PHASE_TIMING, read back with
+// solarosc_debug_read_phases; tools/phase_timing.py prints the averages).
+#ifdef SOLAROSC_PHASE_TIMING
+constexpr int kPhaseSlots = 16, kPhaseCtas = 4096, kPhaseFirst = 8192;
+__device__ long long g_phase[kPhaseSlots * kPhaseCtas];
+#define SOLAROSC_PH(i)                                                                                   \
+    do {                                                                                                 \
+        if (threadIdx.x == 0 && blockIdx.x >= kPhaseFirst && blockIdx.x < kPhaseFirst + kPhaseCtas)      \
+            g_phase[(blockIdx.x - kPhaseFirst) * kPhaseSlots + (i)] = clock64();                         \
+    } while (0)
+#else
+#define SOLAROSC_PH(i)
+#endif
+
 enum RatesMode { kModeLlh = 0, kModeRates = 1, kModePerbin = 2, kModeAsym = 3 };
 
 struct RatesLaunch {
@@ -140,9 +154,20 @@ __device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double
     Seg* seg = reinterpret_cast<Seg*>(buf);
     int2* se = reinterpret_cast<int2*>(buf + 2 * T.n_seg);
     int* order = reinterpret_cast<int*>(buf + 2 * T.n_seg + T.n_paths);
-    for (int t = threadIdx.x; t < T.n_seg; t += blockDim.x) seg[t] = T.seg[t];
-    for (int t = threadIdx.x; t < T.n_paths; t += blockDim.x) se[t] = T.path_se[t];
-    for (int t = threadIdx.x; t < T.n_cosz; t += blockDim.x) order[t] = T.row_order[t];
+    // first pass with all three loads in flight before any store (one L2 round trip instead of three)
+    const int t0 = threadIdx.x;
+    Seg sg{};
+    int2 pe{};
+    int ro = 0;
+    if (t0 < T.n_seg) sg = T.seg[t0];
+    if (t0 < T.n_paths) pe = T.path_se[t0];
+    if (t0 < T.n_cosz) ro = T.row_order[t0];
+    if (t0 < T.n_seg) seg[t0] = sg;
+    if (t0 < T.n_paths) se[t0] = pe;
+    if (t0 < T.n_cosz) order[t0] = ro;
+    for (int t = t0 + blockDim.x; t < T.n_seg; t += blockDim.x) seg[t] = T.seg[t];
+    for (int t = t0 + blockDim.x; t < T.n_paths; t += blockDim.x) se[t] = T.path_se[t];
+    for (int t = t0 + blockDim.x; t < T.n_cosz; t += blockDim.x) order[t] = T.row_order[t];
     return SegTables{seg, se, order};
 }
 
@@ -163,6 +188,7 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     const double p0 = c12sq * c13sq;                     // P_0 = c12^2 c13^2 (osc.jl:196)
     const double c2 = 1.0 - 2.0 * s12sq;                 // cos(2 theta12)
 
+    SOLAROSC_PH(1);
     // ---- phase 1a: one eigen-system per (fine energy, layer)  (osc.jl:466-470, 370-388) --------
     for (int t = threadIdx.x; t < ne * nl; t += blockDim.x) {
         const int k = t / ne, el = t - k * ne;
@@ -200,7 +226,9 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
             }
         }
     }
+    SOLAROSC_PH(2);
     __syncthreads();
+    SOLAROSC_PH(3);
 
     // ---- day rows: block_average(prob_day, 2)  (propagation_osc.jl:133-134) -----------------------
     for (int j = threadIdx.x; j < cb; j += blockDim.x)
@@ -271,6 +299,7 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
         }
         sink.put(1 + G.row_order[zr], i0 + j, acc8 * inv_block, acch * inv_block);   // block_average (propagation_osc.jl:136-137)
     }
+    SOLAROSC_PH(4);
 }
 
 __global__ void __launch_bounds__(kThreads, SOLAROSC_OSC_MINBLOCKS)
@@ -405,15 +434,71 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 
+// Per-point vectors of the fold of detector D: the B-fragment scale vectors (flux, CC cross-section shape:
+// propagation_osc.jl:185-196) and the additive constants with the backgrounds (propagation_bg.jl:36-83; every
+// ES component uses norm_1).  No barriers inside.
+template <int MODE>
+__device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetector& D, const double* __restrict__ p, size_t b,
+                                             double* scr, const RatesOut& O) {
+    const int nT = T.n_etrue, kt = fold_kt(nT);
+    const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
+    const double f8 = p[3], fh = p[4];
+    const double* pd = p + D.param_off;
+    double* scale = scr;
+    double* cst_es = scr + 16 * kt;
+    double* cst_cc = cst_es + 8 * nte;
+    double* bgs_es = cst_cc + 8 * ntc;
+    double* bgs_cc = bgs_es + 8 * nte;
+    // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
+    //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
+    for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
+        double sh = 0.0;
+        if (i < nT) {
+            const double l = D.log_e_norm[i];
+            sh = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
+        }
+        scale[i] = f8; scale[4 * kt + i] = fh;
+        scale[8 * kt + i] = f8 * sh; scale[12 * kt + i] = fh * sh;
+    }
+    for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
+        double acc = 0.0, c = 0.0;
+        if (j < 8 * nte) {
+            if (j < D.n_es) {
+                for (int q = 0; q < D.n_bg_es; ++q) {
+                    const double raw = D.raw_bg_es[q * D.n_es + j];
+                    acc += (D.bg_es_area[q] != 0.0) ? raw * (D.bg_es_area[q] * pd[0]) : raw;
+                }
+                c = fma(f8, D.c8[j], fma(fh, D.ch[j], 0.5 * acc));   // F8 C8 + Fh Ch + BG/2
+                if (MODE == kModeRates && O.bg_es) O.bg_es[b * D.n_es + j] = acc;
+            }
+            cst_es[j] = c;
+            if (MODE == kModeAsym) bgs_es[j] = acc;
+        } else {
+            const int jc = j - 8 * nte;
+            if (jc < D.n_cc) {
+                for (int q = 0; q < D.n_bg_cc; ++q) {
+                    const double raw = D.raw_bg_cc[q * D.n_cc + jc];
+                    acc += (D.bg_cc_norm[q] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[q]] / 2.2e-6) : raw;
+                }
+                c = 0.5 * acc;
+                if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
+            }
+            cst_cc[jc] = c;
+            if (MODE == kModeAsym) bgs_cc[jc] = acc;
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
                                            const double* p8s, const double* phs, int ldp, double* scr,
-                                           const RatesOut& O, double* red, uint32_t* redf) {
+                                           const RatesOut& O, double* red, uint32_t* redf, bool vectors_ready = false) {
+    // vectors_ready: fold_vectors of detector 0 already ran for this point (the fused kernel does it next to the
+    // eigen table, where its load and exp latencies hide behind other warps' work)
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fg = lane >> 2, ft = lane & 3;
-    const double f8 = p[3], fh = p[4];
     // scale vectors of the B fragments, [4*kt] each: ES 8B (F8), ES hep (Fh), CC 8B (F8 s_i), CC hep (Fh s_i)
     double* scale = scr;
     double* cst_es = scr + 16 * kt;          // per reco bin additive constants
@@ -429,50 +514,14 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
     for (int di = 0; di < T.n_det; ++di) {
         if (L.det_only >= 0 && di != L.det_only) continue;
         const DevDetector& D = T.det[di];
-        const double* pd = p + D.param_off;
         const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
         double* cst_cc = cst_es + 8 * nte;
         double* bgs_es = cst_cc + 8 * ntc;       // summed backgrounds per reco bin (asymmetry mode)
         double* bgs_cc = bgs_es + 8 * nte;
         __syncthreads();   // the previous point / detector is done with the scratch; orders the probability tile
-        // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
-        //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
-        for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
-            double sh = 0.0;
-            if (i < nT) {
-                const double l = D.log_e_norm[i];
-                sh = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
-            }
-            scale[i] = f8; scale[4 * kt + i] = fh;
-            scale[8 * kt + i] = f8 * sh; scale[12 * kt + i] = fh * sh;
-        }
-        for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
-            double acc = 0.0, c = 0.0;
-            if (j < 8 * nte) {
-                if (j < D.n_es) {
-                    for (int q = 0; q < D.n_bg_es; ++q) {
-                        const double raw = D.raw_bg_es[q * D.n_es + j];
-                        acc += (D.bg_es_area[q] != 0.0) ? raw * (D.bg_es_area[q] * pd[0]) : raw;
-                    }
-                    c = fma(f8, D.c8[j], fma(fh, D.ch[j], 0.5 * acc));   // F8 C8 + Fh Ch + BG/2
-                    if (MODE == kModeRates && O.bg_es) O.bg_es[b * D.n_es + j] = acc;
-                }
-                cst_es[j] = c;
-                if (MODE == kModeAsym) bgs_es[j] = acc;
-            } else {
-                const int jc = j - 8 * nte;
-                if (jc < D.n_cc) {
-                    for (int q = 0; q < D.n_bg_cc; ++q) {
-                        const double raw = D.raw_bg_cc[q * D.n_cc + jc];
-                        acc += (D.bg_cc_norm[q] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[q]] / 2.2e-6) : raw;
-                    }
-                    c = 0.5 * acc;
-                    if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
-                }
-                cst_cc[jc] = c;
-                if (MODE == kModeAsym) bgs_cc[jc] = acc;
-            }
-        }
+        SOLAROSC_PH(5);
+        const bool have_vectors = vectors_ready && di == (L.det_only >= 0 ? L.det_only : 0);
+        if (!have_vectors) fold_vectors<MODE>(T, D, p, b, scr, O);
         // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
         if (MODE == kModeRates || MODE == kModePerbin)
             for (int ch = 0; ch < 2; ++ch) {
@@ -486,7 +535,9 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                     else if (night) night[b * nZ * nR + (o - nR)] = v;
                 }
             }
-        __syncthreads();
+        SOLAROSC_PH(6);
+        if (!have_vectors) __syncthreads();
+        SOLAROSC_PH(7);
         double part = 0.0;
         double d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;   // asymmetry mode: day / night totals above threshold
         const uint32_t tile_bytes = 8u * (uint32_t)ldp * 8u;   // one 8-row tile of the probability tile
@@ -615,12 +666,14 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         }
         total += part;
     }
+    SOLAROSC_PH(8);
     if (MODE != kModeLlh) return;
     // ---- block reduction (fixed order: deterministic) ----------------------------------------------
     total = warp_sum(total);
     for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
     if (lane == 0) { red[warp] = total; redf[warp] = fl; }
     __syncthreads();
+    SOLAROSC_PH(9);
     if (threadIdx.x == 0) {
         double s = 0.0;
         uint32_t f = 0;
@@ -684,6 +737,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     __shared__ double red[kWarps];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    SOLAROSC_PH(0);
     const int cbs = L.osc_cb;
     double* tbl = smem;
     double* msw = smem + (size_t)kEntry * T.n_layers * 2 * cbs;
@@ -695,6 +749,10 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     const int n_osc = L.n_points / L.group;
     for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
         const double* po = params + (size_t)g * L.group * L.param_stride;
+        // point g*group's fold vectors ride along with the first eigen table (no barrier needed in between: the
+        // scratch was last read before the closing barrier of the previous fold)
+        const int d0 = L.det_only >= 0 ? L.det_only : 0;
+        fold_vectors<MODE>(T, T.det[d0], po, (size_t)g * L.group, scr, O);
         for (int i0 = 0; i0 < nT; i0 += cbs) {
             // the table of the previous chunk is still being read by slower warps; the previous point's fold is
             // done with the probability tile once its closing barrier has been passed
@@ -704,7 +762,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
         for (int q = 0; q < L.group; ++q) {
             const size_t b = (size_t)g * L.group + q;
             // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
-            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf);
+            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf, q == 0);
         }
     }
 }
