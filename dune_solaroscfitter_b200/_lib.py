@@ -14,12 +14,12 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_grad.cuh")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
-    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_rates",
+    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_grad", "solarosc_eval_rates",
     "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
 )
@@ -63,6 +63,7 @@ def load():
     L.solarosc_set_data.argtypes = [H, C.c_int, dp, dp, dp, dp]
     L.solarosc_eval_llh.argtypes = [H, dp, sz, dp, up]
     L.solarosc_eval_llh_grouped.argtypes = [H, dp, sz, sz, dp, up]
+    L.solarosc_eval_llh_grad.argtypes = [H, dp, sz, dp, dp, up]
     L.solarosc_eval_rates.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp, dp, dp]
     L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_asymmetry.argtypes = [H, C.c_int, dp, sz, dp, dp]

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "solarosc_kernels.cuh"
+#include "solarosc_grad.cuh"
 
 using namespace solarosc;
 
@@ -73,6 +73,10 @@ struct solarosc_handle {
     uint32_t* h_flags = nullptr; // pinned, grown on demand (n_points)
     size_t h_flags_n = 0;
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
+    double* d_gradws = nullptr;  // gradient path: probabilities of each point and its shifted copies, then the gradients
+    size_t gradws_bytes = 0;
+    size_t grad_smem = 0;
+    bool grad_ok = false;
     size_t scratch_bytes = 0;
     size_t osc_smem_limit = 200 * 1024;
     size_t fused_smem = 0, seg_bytes = 0;
@@ -337,6 +341,9 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(rates_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
+    h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    h->grad_ok = h->grad_smem <= prop.sharedMemPerBlockOptin;
+    if (h->grad_ok) CK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_smem));
     // Fused kernel: the energy axis is walked in chunks of fused_cb coarse bins, the smallest eigen table that
     // still gives the propagation loop whole passes of work (n_cosz * cb items over kThreads threads), so that
     // SOLAROSC_LLH_MINBLOCKS CTAs fit the SM's shared memory.  SOLAROSC_LLH_CHUNKS overrides the chunk count.
@@ -554,6 +561,52 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     return SOLAROSC_OK;
 }
 
+// lnL and its gradient.  Per chunk: osc_kernel evaluates every point and its 2 n_dir shifted copies into the
+// workspace, grad_kernel folds, differentiates and reduces; lnL, gradient rows and flags come back together.
+int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad, uint32_t* flags) {
+    REQUIRE(params && out_lnl && out_grad, "params, out_lnl and out_grad must not be NULL");
+    REQUIRE(h->grad_ok, "binning too large for the gradient kernel's shared-memory tiles");
+    check_data(h, -1);
+    const DevTables& T = h->T;
+    const int n_dir = 3 + (T.earth_unc ? T.n_layers : 0), n_var = 1 + 2 * n_dir;
+    const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
+    const int step = std::max(1, std::min(h->chunk, 1024));
+    const size_t need = ((size_t)step * n_var * osc_pt + (size_t)step * h->P) * sizeof(double);
+    if (need > h->gradws_bytes) {
+        if (h->d_gradws) CK(cudaFree(h->d_gradws));
+        h->d_gradws = nullptr; h->gradws_bytes = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&h->d_gradws), need));
+        h->gradws_bytes = need;
+    }
+    double* d_var = h->d_gradws;
+    double* d_grad = d_var + (size_t)step * n_var * osc_pt;
+    std::vector<uint32_t> fl(step);
+    bool neg = false;
+    h->launches = 0;
+    for (size_t b0 = 0; b0 < n; b0 += step) {
+        const int nb = (int)std::min<size_t>(step, n - b0);
+        CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_osc(h, h->d_params, nb, 1, nullptr, h->stream, n_var, d_var);
+        GradLaunch G{nb, h->P, h->max_ereco, n_dir, n_var};
+        grad_kernel<<<nb, kThreads, h->grad_smem, h->stream>>>(T, G, h->d_params, d_var, h->d_lnl2[0], d_grad, h->d_flags2[0]);
+        CK(cudaGetLastError());
+        ++h->launches;
+        CK(cudaMemcpyAsync(out_lnl + b0, h->d_lnl2[0], nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_grad + b0 * h->P, d_grad, (size_t)nb * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(fl.data(), h->d_flags2[0], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < nb; ++i) {
+            neg |= (fl[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+            if (flags) flags[b0 + i] = fl[i];
+        }
+    }
+    if (neg) {
+        h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
+        return SOLAROSC_ERR_NEGATIVE_RATE;
+    }
+    return SOLAROSC_OK;
+}
+
 // host transpose of per-point [a][b] blocks into [b][a] (Julia layout) in place via a temporary
 void transpose_blocks(double* x, size_t n, int na, int nb) {
     std::vector<double> tmp((size_t)na * nb);
@@ -601,6 +654,7 @@ void solarosc_destroy(solarosc_handle* h) {
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_gradws) cudaFree(h->d_gradws);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -636,6 +690,11 @@ int solarosc_eval_llh(solarosc_handle* h, const double* params, size_t n, double
 int solarosc_eval_llh_grouped(solarosc_handle* h, const double* params, size_t n, size_t group, double* out,
                               uint32_t* flags) {
     return guarded(h, [&]() { return n == 0 ? (int)SOLAROSC_OK : eval_llh_host(h, params, n, group, out, flags); });
+}
+
+int solarosc_eval_llh_grad(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad,
+                           uint32_t* flags) {
+    return guarded(h, [&]() { return n == 0 ? (int)SOLAROSC_OK : eval_llh_grad_host(h, params, n, out_lnl, out_grad, flags); });
 }
 
 int solarosc_eval_rates(solarosc_handle* h, int det, const double* params, size_t n, double* es_day, double* es_night,

@@ -110,10 +110,10 @@ __host__ __device__ inline size_t llh_smem_bytes(int n_layers, int cb, int n_etr
 
 // Oscillation-stage directions of the gradient path: sin2_th12, sin2_th13, dm2_21, then earth_norm_k.
 __host__ __device__ inline int grad_dir_col(int d) { return d < 3 ? d : SOLAROSC_N_FIXED_PARAMS + (d - 3); }
-// Central-difference half-step of column col.  The probabilities are smooth and carry ~1e-13 of rounding
-// noise, so a step of 1e-6 (absolute; relative 1e-7 for dm2_21, whose phases multiply it by ~1e7) keeps
-// both truncation and noise near 1e-8 of the derivative.
-__host__ __device__ inline double grad_step(int col, const double* p) { return col == 2 ? 1e-7 * p[2] : 1e-6; }
+// Central-difference half-step of column col: 1e-6 relative on dm2_21, 1e-4 absolute on the mixing angles and
+// earth norms.  The probabilities are smooth on these scales and carry ~1e-11 of rounding noise, so truncation and
+// noise both stay near 1e-7 of the derivative (derivation in solarosc_grad.cuh).
+__host__ __device__ inline double grad_step(int col, const double* p) { return col == 2 ? 1e-6 * p[2] : 1e-4; }
 
 // ------------------------------------------------------------------------------------------
 // K1 + K2.  `sink.put(row, i, p8, ph)` receives the block-averaged nu_e survival probabilities of

@@ -103,6 +103,16 @@ class SolarOscEngine:
             self._check(st)
         return (out, fl) if return_flags else out
 
+    def eval_llh_grad(self, params, return_flags: bool = False):
+        """lnL [n] and d lnL / d params [n, P] (what BAT's HMC asks of the log-density, mcmc.jl:102-103)."""
+        p = self._params(params)
+        out, grad = np.empty(len(p)), np.empty((len(p), self.n_params))
+        fl = np.zeros(len(p), dtype=np.uint32)
+        st = self._L.solarosc_eval_llh_grad(self._h, _dp(p), len(p), _dp(out), _dp(grad), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
+        if st != abi.ERR_NEGATIVE_RATE:
+            self._check(st)
+        return (out, grad, fl) if return_flags else (out, grad)
+
     def eval_rates(self, params, det: int = 0) -> Dict[str, np.ndarray]:
         p = self._params(params)
         n = len(p)

@@ -24,6 +24,8 @@
  *   solarosc_eval_llh_grouped  the same for llhScan.jl:84-116, where the n_sys x 3 points of a
  *                          grid cell share one oscillation stage (precomputed_osc,
  *                          propagation_main.jl:60-66)
+ *   solarosc_eval_llh_grad the value + gradient BAT's HMC asks of that log-density (mcmc.jl:102-103, where the
+ *                          reference differentiates total_llh with ForwardDiff)
  *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
  *                          propagation_main.jl:56-157 (exclusive, non-angular branch)
  *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
@@ -159,6 +161,14 @@ int solarosc_eval_llh(solarosc_handle *h, const double *params, size_t n_points,
  * point g*group.  n_points must be a multiple of group. */
 int solarosc_eval_llh_grouped(solarosc_handle *h, const double *params, size_t n_points, size_t group,
                               double *out_lnl, uint32_t *out_flags);
+
+/* lnL and d lnL / d params for every point: out_grad[b*P + k] = d lnL_b / d params[b][k].  Fluxes, cross-section
+ * and background norms are differentiated analytically (reverse mode through the fold); the oscillation columns
+ * (0..2 and earth_norm_*) use central differences of the oscillation stage (relative accuracy ~1e-6).  Columns
+ * the likelihood does not depend on ({det}_ES_bg_norm_2.., which the reference never reads) get 0, as does every
+ * column of a point whose earth norms are out of bounds (lnL = -Inf). */
+int solarosc_eval_llh_grad(solarosc_handle *h, const double *params, size_t n_points, double *out_lnl,
+                           double *out_grad, uint32_t *out_flags);
 
 /* Expected rates of detector det.  Outputs (any may be NULL), batch index slowest:
  *   es_day [n][n_ereco_es], es_night [n][n_cosz][n_ereco_es] (col_major: [n][n_ereco_es][n_cosz]),
