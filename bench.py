@@ -277,6 +277,16 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(dt.item())
 
+    # ---- value + gradient (C3, HMC): 4096 chain points per call through the host-buffer C ABI ---------------
+    grad_value = None
+    if rank == 0:
+        gp = np.ascontiguousarray(params[:: max(1, n // 4096)][:4096])
+        eng.eval_llh_grad(gp)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.eval_llh_grad(gp)
+        grad_value = 3 * len(gp) / (time.perf_counter() - t0)
+
     # ---- parity gate on this run's own output ------------------------------------------------------------
     torch.cuda.synchronize()
     lnl_dev = d_lnl.cpu().numpy()
@@ -331,6 +341,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * P * 8), "d2h_bytes_per_step": int(n * 12)},
         "grouped": {"value": grouped_value, "unit": UNIT, "group": n_cell,
                     "note": "oscillation stage shared by the points of a scan cell (precomputed_osc); not the headline"},
+        "value_and_gradient": {"value": grad_value, "unit": "lnL + gradient evaluations/s", "batch": 4096,
+                               "note": "solarosc_eval_llh_grad from host buffers on one GPU (HMC entry, C3); every evaluation "
+                                       "runs 1 + 2 x 9 oscillation stages; not the headline"},
         "gpu_launches": int(launches), "clocks": clocks,
         "e2e_equals_device_result": same,
     }

@@ -14,7 +14,7 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_grad.cuh")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_grad.cuh", "solarosc_batcher.hpp")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (
@@ -22,7 +22,12 @@ EXPORTS = (
     "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_grad", "solarosc_eval_rates",
     "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
+    "solarosc_batcher_create", "solarosc_batcher_create_with", "solarosc_batcher_eval", "solarosc_batcher_leave",
+    "solarosc_batcher_stats", "solarosc_batcher_destroy",
 )
+
+BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                       C.POINTER(C.c_uint32))
 
 _lib = None
 
@@ -75,5 +80,14 @@ def load():
     L.solarosc_last_timing.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.solarosc_last_fused.argtypes = [H]
     L.solarosc_measure_fp64_peak.argtypes = [H, dp]
+    L.solarosc_batcher_create.argtypes = [H, C.c_int, C.c_int, C.c_int]
+    L.solarosc_batcher_create.restype = C.c_void_p
+    L.solarosc_batcher_create_with.argtypes = [BATCH_FN, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.solarosc_batcher_create_with.restype = C.c_void_p
+    L.solarosc_batcher_eval.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, up]
+    L.solarosc_batcher_leave.argtypes = [C.c_void_p, C.c_int]
+    L.solarosc_batcher_stats.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.solarosc_batcher_destroy.argtypes = [C.c_void_p]
+    L.solarosc_batcher_destroy.restype = None
     _lib = L
     return L

@@ -908,3 +908,5 @@ int solarosc_measure_fp64_peak(solarosc_handle* h, double* tflops) {
 }
 
 }  // extern "C"
+
+#include "solarosc_batcher.hpp"

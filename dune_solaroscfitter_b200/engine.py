@@ -174,6 +174,10 @@ class SolarOscEngine:
                                                  fl.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def batcher(self, n_participants: int, want_grad: bool = False, max_wait_ms: int = 0) -> "Batcher":
+        """Rendezvous for n single-point callers (one per chain thread): see include/solarosc_b200.h."""
+        return Batcher(self, n_participants, want_grad, max_wait_ms)
+
     def set_timing(self, enabled: bool = True):
         self._check(self._L.solarosc_set_timing(self._h, int(enabled)))
 
@@ -186,3 +190,42 @@ class SolarOscEngine:
         a, b = C.c_float(0), C.c_float(0)
         n = self._L.solarosc_last_timing(self._h, C.byref(a), C.byref(b))
         return dict(ms_osc=a.value, ms_rates=b.value, launches=n, fused=bool(self._L.solarosc_last_fused(self._h)))
+
+
+class Batcher:
+    """N threads each call ``eval(slot, params)`` with ONE point; one batched launch serves them all."""
+
+    def __init__(self, engine: SolarOscEngine, n_participants: int, want_grad: bool = False, max_wait_ms: int = 0):
+        self._L, self._engine = engine._L, engine   # the handle must outlive the batcher
+        self.n_params, self.want_grad = engine.n_params, bool(want_grad)
+        self._b = self._L.solarosc_batcher_create(engine._h, n_participants, int(want_grad), max_wait_ms)
+        if not self._b:
+            raise SolarOscError(abi.ERR_ARG, "solarosc_batcher_create failed")
+
+    def eval(self, slot: int, params):
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(self.n_params)
+        lnl, fl = C.c_double(), C.c_uint32()
+        g = np.empty(self.n_params) if self.want_grad else None
+        st = self._L.solarosc_batcher_eval(self._b, slot, _dp(p), C.byref(lnl), _dp(g), C.byref(fl))
+        if st not in (abi.OK, abi.ERR_NEGATIVE_RATE):
+            raise SolarOscError(st, "solarosc_batcher_eval failed")
+        return (lnl.value, g) if self.want_grad else lnl.value
+
+    def leave(self, slot: int):
+        self._L.solarosc_batcher_leave(self._b, slot)
+
+    def stats(self):
+        nb, npnt = C.c_ulonglong(), C.c_ulonglong()
+        self._L.solarosc_batcher_stats(self._b, C.byref(nb), C.byref(npnt))
+        return nb.value, npnt.value
+
+    def close(self):
+        if getattr(self, "_b", None):
+            self._L.solarosc_batcher_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -174,6 +174,15 @@ class SolarOscSession:
     def total_llh_batch(self, params, group: int = 1) -> np.ndarray:
         return self.engine.eval_llh(self.pack_many(params), group=group, raise_on_negative=True)
 
+    def total_llh_and_grad_batch(self, params):
+        """lnL [n] and d lnL / d params [n, P]: the value + gradient BAT's HMC takes from the log-density where the
+        reference differentiates total_llh with ForwardDiff (mcmc.jl:102-103)."""
+        return self.engine.eval_llh_grad(self.pack_many(params))
+
+    def total_llh_and_grad(self, params):
+        lnl, grad = self.total_llh_and_grad_batch([params])
+        return float(lnl[0]), dict(zip(self.engine.param_names, grad[0]))
+
     def per_bin_llh(self, params, det: int = 0) -> Dict[str, np.ndarray]:
         r = self.engine.eval_perbin(self.pack_many(params), det)
         return {k: v[0] for k, v in r.items()}

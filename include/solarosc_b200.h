@@ -207,6 +207,28 @@ int solarosc_eval_llh_device(solarosc_handle *h, const double *d_params, size_t 
 int solarosc_poisson_llh(solarosc_handle *h, const double *expected, const double *measured, size_t n_vec,
                          size_t len, double *out, uint32_t *out_flags);
 
+/*
+ * Rendezvous batching for hosts that evaluate one point per thread (BAT's chains on Julia threads call
+ * logdensityof(likelihood, params) one point at a time, mcmc.jl:96-110, likelihood_main.jl:37-39): each of
+ * n_participants threads owns a slot and calls solarosc_batcher_eval with its point; the call blocks until every
+ * participant that has not left is waiting (or until max_wait_ms > 0 has elapsed for some waiter), then ONE
+ * batched evaluation serves them all.  want_grad selects solarosc_eval_llh_grad (out_grad [P]) over
+ * solarosc_eval_llh.  The return value is the status of the batched call.  solarosc_batcher_leave retires a slot
+ * (a chain that has finished) so the others stop waiting for it.  solarosc_batcher_create_with takes any
+ * evaluator with the same contract (tests drive the rendezvous logic with a CPU stand-in).
+ */
+typedef struct solarosc_batcher solarosc_batcher;
+typedef int (*solarosc_batch_fn)(void *ctx, const double *params, size_t n_points, double *out_lnl, double *out_grad,
+                                 uint32_t *out_flags);
+solarosc_batcher *solarosc_batcher_create(solarosc_handle *h, int n_participants, int want_grad, int max_wait_ms);
+solarosc_batcher *solarosc_batcher_create_with(solarosc_batch_fn fn, void *ctx, int n_params, int n_participants,
+                                               int want_grad, int max_wait_ms);
+int solarosc_batcher_eval(solarosc_batcher *b, int slot, const double *params, double *out_lnl, double *out_grad,
+                          uint32_t *out_flag);
+int solarosc_batcher_leave(solarosc_batcher *b, int slot);
+int solarosc_batcher_stats(solarosc_batcher *b, unsigned long long *n_batches, unsigned long long *n_points);
+void solarosc_batcher_destroy(solarosc_batcher *b);
+
 /* Per-kernel device timing.  When enabled, eval_llh / eval_llh_grouped / eval_llh_device record CUDA
  * events around each kernel on the launching stream; solarosc_last_timing waits for the last one and
  * returns the summed durations [ms] of the oscillation kernel and of the rate+likelihood kernel of

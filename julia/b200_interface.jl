@@ -188,6 +188,53 @@ end
 total_llh(parameters) = total_llh_batch([parameters])[1]
 
 """
+    total_llh_and_grad_batch(params) -> (lnL::Vector, grad::Matrix)   # grad is P x B
+
+Value and gradient of `total_llh` for every point: what BAT's HMC needs from the log-density in place of the
+ForwardDiff pass of mcmc.jl:102-103.  Row k of `grad` belongs to column k of `pack` (see `param_names`).
+"""
+function total_llh_and_grad_batch(params)
+    M = pack_many(params); B = size(M, 2)
+    out = Vector{Float64}(undef, B); grad = Matrix{Float64}(undef, size(M, 1), B); flags = Vector{UInt32}(undef, B)
+    GC.@preserve M out grad flags begin
+        check(@ccall libb200.solarosc_eval_llh_grad(handle[]::Handle, pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t,
+                                                    pointer(out)::Ptr{Cdouble}, pointer(grad)::Ptr{Cdouble},
+                                                    pointer(flags)::Ptr{UInt32})::Cint)
+    end
+    return out, grad
+end
+
+# ---- rendezvous for BAT's chain threads ---------------------------------------------------------------------------
+# BAT evaluates logdensityof(likelihood, params) one point per chain thread (mcmc.jl:96-110).  Each chain thread
+# takes slot Threads.threadid() - 1; solarosc_batcher_eval blocks until all chains still running have deposited
+# their point, then one launch serves them.  With DensityInterface + ChangesOfVariables a
+# `logdensity_and_gradient` method built on chain_llh_and_grad replaces the ForwardDiff wrapper.
+const batcher = Ref{Ptr{Cvoid}}(C_NULL)
+
+function start_batcher(n_chains::Int; want_grad::Bool=true, max_wait_ms::Int=0)
+    batcher[] = @ccall libb200.solarosc_batcher_create(handle[]::Handle, Cint(n_chains)::Cint, Cint(want_grad)::Cint,
+                                                       Cint(max_wait_ms)::Cint)::Ptr{Cvoid}
+    batcher[] == C_NULL && error("solarosc_batcher_create failed")
+    return nothing
+end
+
+"lnL and gradient of ONE point from chain `slot` (0-based); blocks until the batch it joined has run."
+function chain_llh_and_grad(parameters, slot::Int=Threads.threadid() - 1)
+    row = pack(parameters); lnl = Ref{Cdouble}(0.0); grad = Vector{Float64}(undef, length(row)); fl = Ref{UInt32}(0)
+    GC.@preserve row grad begin
+        # @threadcall would hand the wait to a libuv worker; plain @ccall keeps the Julia thread parked in C, which
+        # is what the reference's NuFast wrapper does as well (nuFast_interface.jl:94-127)
+        st = @ccall libb200.solarosc_batcher_eval(batcher[]::Ptr{Cvoid}, Cint(slot)::Cint, pointer(row)::Ptr{Cdouble},
+                                                  lnl::Ref{Cdouble}, pointer(grad)::Ptr{Cdouble}, fl::Ref{UInt32})::Cint
+        check(st)
+    end
+    return lnl[], grad
+end
+
+chain_done(slot::Int=Threads.threadid() - 1) = (@ccall libb200.solarosc_batcher_leave(batcher[]::Ptr{Cvoid}, Cint(slot)::Cint)::Cint; nothing)
+stop_batcher() = (batcher[] != C_NULL && (@ccall libb200.solarosc_batcher_destroy(batcher[]::Ptr{Cvoid})::Cvoid); batcher[] = C_NULL; nothing)
+
+"""
     propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc, verbose)
 
 Same signature and 7-tuple as propagation_main.jl:56-157 (exclusive, non-angular branch).  The table

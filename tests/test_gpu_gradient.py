@@ -86,3 +86,29 @@ def test_gradient_directional_consistency(engine, tables, draw):
     up, dn = engine.eval_llh(p + v), engine.eval_llh(p - v)
     pred = 2 * np.sum(grad * v, axis=1)
     assert np.max(np.abs((up - dn) - pred) / np.maximum(np.abs(pred), 1e-3)) < 1e-3
+
+
+def test_batcher_serves_chain_threads(engine, tables, draw):
+    """Eight 'chain' threads with one point each per step: the rendezvous launches one batch per step and every
+    thread gets the value and gradient the batched call gives for its point."""
+    import threading
+    n, steps = 8, 5
+    pts = draw(tables, n * steps).reshape(steps, n, -1)
+    ref_l, ref_g = engine.eval_llh_grad(pts.reshape(n * steps, -1))
+    ref_l, ref_g = ref_l.reshape(steps, n), ref_g.reshape(steps, n, -1)
+    bat = engine.batcher(n, want_grad=True)
+    got = {}
+
+    def chain(slot):
+        for s in range(steps):
+            got[(s, slot)] = bat.eval(slot, pts[s, slot])
+        bat.leave(slot)
+
+    th = [threading.Thread(target=chain, args=(k,)) for k in range(n)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not any(t.is_alive() for t in th)
+    assert bat.stats() == (steps, n * steps)
+    for (s, slot), (l, g) in got.items():
+        assert l == ref_l[s, slot] and np.array_equal(g, ref_g[s, slot])
+    bat.close()
