@@ -82,7 +82,22 @@ static const double kTrigHost[16] = {SOLAROSC_TRIG_TABLE};
 #if defined(__CUDA_ARCH__)
 #define SOLAROSC_HD __host__ __device__ __forceinline__
 #define SOLAROSC_TRIG(i) kTrigDev[i]
-__device__ __forceinline__ double rsq(double x) { return rsqrt(x); }
+// 1/sqrt(x) and 1/x of a positive normal double: hardware seed (22 bits) and two Newton steps, no special cases --
+// about a third of the instructions of rsqrt() / a division, and straight-line code that the scheduler can
+// interleave with its neighbours.  Within 1-2 ulp.
+__device__ __forceinline__ double rsq(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return fma(y, fma(-hx * y, y, 0.5), y);
+}
+__device__ __forceinline__ double rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(fma(-x, y, 1.0), y, y);
+    return fma(fma(-x, y, 1.0), y, y);
+}
 __device__ __forceinline__ int lo_int(double x) { return __double2loint(x); }
 // x with its sign flipped when `flip` has bit 31 set: an integer XOR, not an FP64-pipe negation
 __device__ __forceinline__ double flip_sign(double x, int flip) {
@@ -94,6 +109,7 @@ __device__ __forceinline__ double flip_sign(double x, int flip) {
 #define SOLAROSC_HD __host__ __device__ inline
 #define SOLAROSC_TRIG(i) kTrigHost[i]
 inline double rsq(double x) { return 1.0 / std::sqrt(x); }
+inline double rcp(double x) { return 1.0 / x; }
 inline int lo_int(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(uint32_t)(b & 0xffffffff); }
 inline double flip_sign(double x, int flip) { return (flip & 0x80000000) ? -x : x; }
 #endif
@@ -148,32 +164,35 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
     const double u[3] = {u1, u2, u3};
     double s11 = a * u1 * u1, s22 = fma(a * u2, u2, d21), s33 = fma(a * u3, u3, d31);
     double s12 = a * u1 * u2, s13 = a * u1 * u3, s23 = a * u2 * u3;
+    // Written without branches (selects only), so that two eigen-systems in flight interleave.
     double mu[3];
-    double p1 = s12 * s12 + s13 * s13 + s23 * s23;
-    if (p1 == 0.0) {
-        mu[0] = s11; mu[1] = s22; mu[2] = s33;
-    } else {
-        double tq = (s11 + s22 + s33) * (1.0 / 3.0);
+    const double p1 = s12 * s12 + s13 * s13 + s23 * s23;
+    {
+        const double tq = (s11 + s22 + s33) * (1.0 / 3.0);
         double b11 = s11 - tq, b22 = s22 - tq, b33 = s33 - tq;
-        double p2 = b11 * b11 + b22 * b22 + b33 * b33 + 2.0 * p1;
-        double p = sqrt(p2 * (1.0 / 6.0));
-        double ip = 1.0 / p;
+        const double p2 = (b11 * b11 + b22 * b22 + b33 * b33 + 2.0 * p1) * (1.0 / 6.0);
+        const double ip = rsq(p2), p = p2 * ip;      // p = sqrt(p2); p2 == 0 only on the diagonal shortcut below
         b11 *= ip; b22 *= ip; b33 *= ip;
-        double c12 = s12 * ip, c13 = s13 * ip, c23 = s23 * ip;
-        double det = b11 * (b22 * b33 - c23 * c23) - c12 * (c12 * b33 - c23 * c13) + c13 * (c12 * c23 - b22 * c13);
-        double r = fmin(1.0, fmax(-1.0, 0.5 * det));
-        double phi = acos(r) * (1.0 / 3.0);
+        const double c12 = s12 * ip, c13 = s13 * ip, c23 = s23 * ip;
+        const double det = b11 * (b22 * b33 - c23 * c23) - c12 * (c12 * b33 - c23 * c13) + c13 * (c12 * c23 - b22 * c13);
+        const double r = fmin(1.0, fmax(-1.0, 0.5 * det));
+        const double phi = acos(r) * (1.0 / 3.0);
         double sp, cp;
         sincos_phase(phi, sp, cp);
         // cos(phi + 2pi/3) = -cp/2 - sqrt(3)/2 * sp
-        mu[2] = fma(2.0 * p, cp, tq);
-        mu[0] = fma(2.0 * p, fma(-0.8660254037844386, sp, -0.5 * cp), tq);
-        mu[1] = 3.0 * tq - mu[0] - mu[2];
+        const double hi = fma(2.0 * p, cp, tq);
+        const double lo = fma(2.0 * p, fma(-0.8660254037844386, sp, -0.5 * cp), tq);
+        const bool diag = p1 == 0.0;                 // no coupling at all: the diagonal is the spectrum
+        mu[2] = diag ? s33 : hi;
+        mu[0] = diag ? s11 : lo;
+        mu[1] = diag ? s22 : 3.0 * tq - lo - hi;
     }
     // ascending order (only needed on the diagonal shortcut, cheap)
-    if (mu[0] > mu[1]) { double t = mu[0]; mu[0] = mu[1]; mu[1] = t; }
-    if (mu[1] > mu[2]) { double t = mu[1]; mu[1] = mu[2]; mu[2] = t; }
-    if (mu[0] > mu[1]) { double t = mu[0]; mu[0] = mu[1]; mu[1] = t; }
+    {
+        double t = fmin(mu[0], mu[1]); mu[1] = fmax(mu[0], mu[1]); mu[0] = t;
+        t = fmin(mu[1], mu[2]); mu[2] = fmax(mu[1], mu[2]); mu[1] = t;
+        t = fmin(mu[0], mu[1]); mu[1] = fmax(mu[0], mu[1]); mu[0] = t;
+    }
     // Root i sits next to pole m_i (interlacing).  Its shift delta_i = mu_i - m_i is re-derived from
     // the secular equation 1 + a sum_k u_k^2/(m_k - mu) = 0, solved for the i-th term:
     //     delta_i = a u_i^2 g_k g_l / (g_k g_l + a (u_k^2 g_l + u_l^2 g_k)),   g_x = m_x - mu_i,
@@ -187,18 +206,16 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
         const double gk = m[k] - mu[i], gl = m[l] - mu[i];
         const double den = fma(a, fma(u[k] * u[k], gl, u[l] * u[l] * gk), gk * gl);
         const double num = a * u[i] * u[i] * gk * gl;
-        const double d = (den != 0.0) ? num / den : mu[i] - m[i];
+        const double d = (den != 0.0) ? num * rcp(den) : mu[i] - m[i];
         dl[i] = d;
         // eigenvector: v[j] ~ u_j prod_{x != j} (mu_i - m_x)
         const double vi = u[i] * (gk * gl), vk = -u[k] * (d * gl), vl = -u[l] * (d * gk);
         const double n2 = vi * vi + vk * vk + vl * vl;
+        // an exactly decoupled state (u_i == 0), or everything underflowed, is the unit vector e_i
+        const bool ok = n2 > 0.0 && n2 < 1e300;
+        const double rn = rsq(ok ? n2 : 1.0);
         double e[3];
-        if (n2 > 0.0 && n2 < 1e300) {
-            const double rn = rsq(n2);
-            e[i] = vi * rn; e[k] = vk * rn; e[l] = vl * rn;
-        } else {  // exactly decoupled state (u_i == 0), or everything underflowed
-            e[i] = 1.0; e[k] = 0.0; e[l] = 0.0;
-        }
+        e[i] = ok ? vi * rn : 1.0; e[k] = ok ? vk * rn : 0.0; e[l] = ok ? vl * rn : 0.0;
         q[0 + i] = e[0]; q[3 + i] = e[1]; q[6 + i] = e[2];
     }
     w2 = (m[1] - m[0]) + (dl[1] - dl[0]);

@@ -190,13 +190,22 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
 
     SOLAROSC_PH(1);
     // ---- phase 1a: one eigen-system per (fine energy, layer)  (osc.jl:466-470, 370-388) --------
-    for (int t = threadIdx.x; t < ne * nl; t += blockDim.x) {
-        const int k = t / ne, el = t - k * ne;
-        const double e = T.e_calc[2 * i0 + el];
-        const double norm = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + k] + (vcol == SOLAROSC_N_FIXED_PARAMS + k ? vdelta : 0.0) : 1.0;
-        const double a = norm * T.earth_lookup[k] * e;   // lookup = earth_norm .* earth_lookup (propagation_osc.jl:60)
-        const int slot = (el & 1) * cbs + (el >> 1);
-        make_entry(dm21, a, e, u1, u2, u3, tbl + ((size_t)k * 2 * cbs + slot) * kEntry);
+    // two entries per thread and pass: make_entry is branch-free, so the two dependency chains interleave
+    for (int t = threadIdx.x; t < ne * nl; t += 2 * blockDim.x) {
+        const int tb = min(t + (int)blockDim.x, ne * nl - 1);   // a thread without a second entry repeats the last one
+        const int ka = t / ne, ela = t - ka * ne, kb = tb / ne, elb = tb - kb * ne;
+        const double ea = T.e_calc[2 * i0 + ela], eb = T.e_calc[2 * i0 + elb];
+        const double na = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + ka] + (vcol == SOLAROSC_N_FIXED_PARAMS + ka ? vdelta : 0.0) : 1.0;
+        const double nb = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + kb] + (vcol == SOLAROSC_N_FIXED_PARAMS + kb ? vdelta : 0.0) : 1.0;
+        // lookup = earth_norm .* earth_lookup (propagation_osc.jl:60)
+        const double aa = na * T.earth_lookup[ka] * ea, ab = nb * T.earth_lookup[kb] * eb;
+        double enta[kEntry], entb[kEntry];
+        make_entry(dm21, aa, ea, u1, u2, u3, enta);
+        make_entry(dm21, ab, eb, u1, u2, u3, entb);
+        double* da = tbl + ((size_t)ka * 2 * cbs + (ela & 1) * cbs + (ela >> 1)) * kEntry;
+        double* db = tbl + ((size_t)kb * 2 * cbs + (elb & 1) * cbs + (elb >> 1)) * kEntry;
+#pragma unroll
+        for (int x = 0; x < kEntry; ++x) { da[x] = enta[x]; db[x] = entb[x]; }   // same values when tb repeats another thread's entry
     }
     // ---- phase 1b: MSW day probability and cos(2 theta_m) per (process, fine energy) ------------
     if (T.fast) {  // osc.jl:185-207 with n_e = production-weighted mean density
