@@ -171,6 +171,10 @@ __device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double
     return SegTables{seg, se, order};
 }
 
+__device__ __forceinline__ double sqrt_pos(double x);
+// square root of a number in [0, 1] (exactly 0 at 0), straight-line
+__device__ __forceinline__ double sqrt01(double x) { return x > 0.0 ? sqrt_pos(x) : 0.0; }
+
 template <class Sink>
 __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G, const double* __restrict__ p, int i0, int cb,
                                           int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink,
@@ -183,8 +187,8 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     const double s13sq = fmin(fmax(p[1] + (vcol == 1 ? vdelta : 0.0), 0.0), 1.0);
     const double dm21 = p[2] + (vcol == 2 ? vdelta : 0.0);
     const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq;
-    const double c13 = sqrt(c13sq);
-    const double u1 = sqrt(c12sq) * c13, u2 = sqrt(s12sq) * c13, u3 = sqrt(s13sq);
+    const double c13 = sqrt01(c13sq);
+    const double u1 = sqrt01(c12sq) * c13, u2 = sqrt01(s12sq) * c13, u3 = sqrt01(s13sq);
     const double p0 = c12sq * c13sq;                     // P_0 = c12^2 c13^2 (osc.jl:196)
     const double c2 = 1.0 - 2.0 * s12sq;                 // cos(2 theta12)
 
@@ -487,7 +491,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
             if (jc < D.n_cc) {
                 for (int q = 0; q < D.n_bg_cc; ++q) {
                     const double raw = D.raw_bg_cc[q * D.n_cc + jc];
-                    acc += (D.bg_cc_norm[q] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[q]] / 2.2e-6) : raw;
+                    acc += (D.bg_cc_norm[q] >= 0) ? raw * (pd[D.n_norm_es + D.bg_cc_norm[q]] * (1.0 / 2.2e-6)) : raw;
                 }
                 c = 0.5 * acc;
                 if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
