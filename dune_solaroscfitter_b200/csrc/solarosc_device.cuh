@@ -229,9 +229,11 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
 // so q_0 and the common phase are never needed (reference osc_kernel, osc.jl:360-364, applied to a
 // vector instead of forming the 3x3 products of osc.jl:442).
 //   [0..2] q_1   [3..5] q_2   [6] c*(mu_1-mu_0)/E   [7] c*(mu_2-mu_0)/E   [8] q_1.u   [9] q_2.u
-// The stride of 11 doubles keeps the per-lane 8-byte loads of consecutive energies bank-conflict free.
+// Ten doubles = 80 bytes: entries are 16-byte aligned, so a step fetches its eight numbers with four 128-bit
+// loads, and the 80-byte pitch between the entries of consecutive energies (the lanes of a warp) keeps every
+// quarter-warp of such a load on distinct banks.
 // ------------------------------------------------------------------------------------------
-constexpr int kEntry = 11;
+constexpr int kEntry = 10;
 
 SOLAROSC_HD void make_entry(double dm21, double a, double e_gev, double u1, double u2, double u3, double* ent) {
     double q[9], w2, w3;
@@ -242,53 +244,75 @@ SOLAROSC_HD void make_entry(double dm21, double a, double e_gev, double u1, doub
     ent[6] = f * w2; ent[7] = f * w3;
     ent[8] = fma(q[7], u3, fma(q[4], u2, q[1] * u1));
     ent[9] = fma(q[8], u3, fma(q[5], u2, q[2] * u1));
-    ent[10] = 0.0;
 }
 
 struct State { double ar, ai, br, bi, cr, ci; };
 
+// what a layer step needs of an entry, fetched with 128-bit loads
+struct Ent {
+    double q1x, q1y, q1z, q2x, q2y, q2z, k1, k2;
+};
+SOLAROSC_HD Ent load_ent(const double* e) {
+    const double2* v = reinterpret_cast<const double2*>(e);
+    const double2 a = v[0], b = v[1], c = v[2], d = v[3];
+    return Ent{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+
 // y_n = e^{-i phi_n} - 1 for both excited eigenstates of this entry
-SOLAROSC_HD void step_phases(const double* e, double len, double& y1r, double& y1i, double& y2r, double& y2i) {
+SOLAROSC_HD void step_phases(const Ent& e, double len, double& y1r, double& y1i, double& y2r, double& y2i) {
     double s1, c1, s2, c2;
-    sincos_phase(len * e[6], s1, c1);
-    sincos_phase(len * e[7], s2, c2);
+    sincos_phase(len * e.k1, s1, c1);
+    sincos_phase(len * e.k2, s2, c2);
     y1r = c1 - 1.0; y1i = -s1; y2r = c2 - 1.0; y2i = -s2;
 }
 
 // first step of a path: psi = u is real, q_n.u is tabulated
-SOLAROSC_HD void step_first(const double* e, double len, double u1, double u2, double u3, State& p) {
+SOLAROSC_HD void step_first(const double* ep, double len, double u1, double u2, double u3, State& p) {
+    const Ent e = load_ent(ep);
+    const double2 d = reinterpret_cast<const double2*>(ep)[4];
     double y1r, y1i, y2r, y2i;
     step_phases(e, len, y1r, y1i, y2r, y2i);
-    const double t1r = y1r * e[8], t1i = y1i * e[8], t2r = y2r * e[9], t2i = y2i * e[9];
-    p.ar = fma(e[3], t2r, fma(e[0], t1r, u1)); p.ai = fma(e[3], t2i, e[0] * t1i);
-    p.br = fma(e[4], t2r, fma(e[1], t1r, u2)); p.bi = fma(e[4], t2i, e[1] * t1i);
-    p.cr = fma(e[5], t2r, fma(e[2], t1r, u3)); p.ci = fma(e[5], t2i, e[2] * t1i);
+    const double t1r = y1r * d.x, t1i = y1i * d.x, t2r = y2r * d.y, t2i = y2i * d.y;
+    p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, u1)); p.ai = fma(e.q2x, t2i, e.q1x * t1i);
+    p.br = fma(e.q2y, t2r, fma(e.q1y, t1r, u2)); p.bi = fma(e.q2y, t2i, e.q1y * t1i);
+    p.cr = fma(e.q2z, t2r, fma(e.q1z, t1r, u3)); p.ci = fma(e.q2z, t2i, e.q1z * t1i);
+}
+
+// the only step of a one-layer path: first and last at once, only the nu_1 component is formed
+SOLAROSC_HD void step_only(const double* ep, double len, double u1, State& p) {
+    const Ent e = load_ent(ep);
+    const double2 d = reinterpret_cast<const double2*>(ep)[4];
+    double y1r, y1i, y2r, y2i;
+    step_phases(e, len, y1r, y1i, y2r, y2i);
+    p.ar = fma(e.q2x, y2r * d.y, fma(e.q1x, y1r * d.x, u1));
+    p.ai = fma(e.q2x, y2i * d.y, e.q1x * (y1i * d.x));
 }
 
 // t_n = y_n * (q_n . psi)
-SOLAROSC_HD void step_project(const double* e, double len, const State& p, double& t1r, double& t1i, double& t2r,
-                              double& t2i) {
+SOLAROSC_HD void step_project(const Ent& e, double len, const State& p, double& t1r, double& t1i, double& t2r, double& t2i) {
     double y1r, y1i, y2r, y2i;
     step_phases(e, len, y1r, y1i, y2r, y2i);
-    const double w1r = fma(e[2], p.cr, fma(e[1], p.br, e[0] * p.ar)), w1i = fma(e[2], p.ci, fma(e[1], p.bi, e[0] * p.ai));
-    const double w2r = fma(e[5], p.cr, fma(e[4], p.br, e[3] * p.ar)), w2i = fma(e[5], p.ci, fma(e[4], p.bi, e[3] * p.ai));
+    const double w1r = fma(e.q1z, p.cr, fma(e.q1y, p.br, e.q1x * p.ar)), w1i = fma(e.q1z, p.ci, fma(e.q1y, p.bi, e.q1x * p.ai));
+    const double w2r = fma(e.q2z, p.cr, fma(e.q2y, p.br, e.q2x * p.ar)), w2i = fma(e.q2z, p.ci, fma(e.q2y, p.bi, e.q2x * p.ai));
     t1r = fma(-y1i, w1i, y1r * w1r); t1i = fma(y1i, w1r, y1r * w1i);
     t2r = fma(-y2i, w2i, y2r * w2r); t2i = fma(y2i, w2r, y2r * w2i);
 }
 
-SOLAROSC_HD void step_mid(const double* e, double len, State& p) {
+SOLAROSC_HD void step_mid(const double* ep, double len, State& p) {
+    const Ent e = load_ent(ep);
     double t1r, t1i, t2r, t2i;
     step_project(e, len, p, t1r, t1i, t2r, t2i);
-    p.ar = fma(e[3], t2r, fma(e[0], t1r, p.ar)); p.ai = fma(e[3], t2i, fma(e[0], t1i, p.ai));
-    p.br = fma(e[4], t2r, fma(e[1], t1r, p.br)); p.bi = fma(e[4], t2i, fma(e[1], t1i, p.bi));
-    p.cr = fma(e[5], t2r, fma(e[2], t1r, p.cr)); p.ci = fma(e[5], t2i, fma(e[2], t1i, p.ci));
+    p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, p.ar)); p.ai = fma(e.q2x, t2i, fma(e.q1x, t1i, p.ai));
+    p.br = fma(e.q2y, t2r, fma(e.q1y, t1r, p.br)); p.bi = fma(e.q2y, t2i, fma(e.q1y, t1i, p.bi));
+    p.cr = fma(e.q2z, t2r, fma(e.q1z, t1r, p.cr)); p.ci = fma(e.q2z, t2i, fma(e.q1z, t1i, p.ci));
 }
 
 // last step: only the nu_1 component of the state is read afterwards
-SOLAROSC_HD void step_last(const double* e, double len, State& p) {
+SOLAROSC_HD void step_last(const double* ep, double len, State& p) {
+    const Ent e = load_ent(ep);
     double t1r, t1i, t2r, t2i;
     step_project(e, len, p, t1r, t1i, t2r, t2i);
-    p.ar = fma(e[3], t2r, fma(e[0], t1r, p.ar)); p.ai = fma(e[3], t2i, fma(e[0], t1i, p.ai));
+    p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, p.ar)); p.ai = fma(e.q2x, t2i, fma(e.q1x, t1i, p.ai));
 }
 
 // P(nu_1 -> nu_e) of one path at one energy.  tbl points at the entry of layer 0 for this energy,
@@ -298,10 +322,7 @@ SOLAROSC_HD double path_p1e(const double* tbl, size_t layer_stride, const int* a
     State p;
     const double* e = tbl + (size_t)app_layer[s0] * layer_stride;
     if (s1 - s0 == 1) {   // one layer: first and last step at once
-        double y1r, y1i, y2r, y2i;
-        step_phases(e, app_len[s0], y1r, y1i, y2r, y2i);
-        const double t1r = y1r * e[8], t1i = y1i * e[8], t2r = y2r * e[9], t2i = y2i * e[9];
-        p.ar = fma(e[3], t2r, fma(e[0], t1r, u1)); p.ai = fma(e[3], t2i, e[0] * t1i);
+        step_only(e, app_len[s0], u1, p);
     } else {
         step_first(e, app_len[s0], u1, u2, u3, p);
         for (int s = s0 + 1; s < s1 - 1; ++s) step_mid(tbl + (size_t)app_layer[s] * layer_stride, app_len[s], p);

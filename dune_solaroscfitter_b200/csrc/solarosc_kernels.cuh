@@ -143,6 +143,17 @@ struct SegTables {
     const int2* path_se;    // [n_cosz * n_sub] (first, one-past-last) step of the paths of sorted row zr
     const int* row_order;   // [n_cosz] zenith bin of sorted row zr
 };
+// One step's (layer, length).  SMEM: the tables are known to sit in shared memory, so the load is an LDS instead
+// of a generic load that has to resolve its address space first -- it feeds the table address of the next step.
+template <bool SMEM>
+__device__ __forceinline__ Seg load_seg(const SegTables& G, int s) {
+    if (!SMEM) return G.seg[s];
+    Seg r;
+    long long bits;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(r.len), "=l"(bits) : "r"((uint32_t)__cvta_generic_to_shared(G.seg + s)));
+    r.layer = (int)bits; r.pad = 0;
+    return r;
+}
 
 __host__ __device__ inline size_t seg_smem_doubles(int n_seg, int n_paths, int n_cosz) {
     return (size_t)2 * n_seg + n_paths + ((size_t)n_cosz + 1) / 2 + 1;
@@ -175,7 +186,7 @@ __device__ __forceinline__ double sqrt_pos(double x);
 // square root of a number in [0, 1] (exactly 0 at 0), straight-line
 __device__ __forceinline__ double sqrt01(double x) { return x > 0.0 ? sqrt_pos(x) : 0.0; }
 
-template <class Sink>
+template <bool SEG_SMEM, class Sink>
 __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G, const double* __restrict__ p, int i0, int cb,
                                           int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink,
                                           int vcol = -1, double vdelta = 0.0) {
@@ -271,25 +282,20 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
             // The (layer, length) of the next step is fetched while the current one is computed.
             State pa, pb;
             {
-                Seg sg = G.seg[s0];
+                Seg sg = load_seg<SEG_SMEM>(G, s0);
                 const int k = sg.layer * ls;
                 const double len = sg.len;
                 if (s1 - s0 == 1) {
-                    double y1r, y1i, y2r, y2i;
-                    step_phases(t0 + k, len, y1r, y1i, y2r, y2i);
-                    pa.ar = fma(t0[k + 3], y2r * t0[k + 9], fma(t0[k], y1r * t0[k + 8], u1));
-                    pa.ai = fma(t0[k + 3], y2i * t0[k + 9], t0[k] * (y1i * t0[k + 8]));
-                    step_phases(t1 + k, len, y1r, y1i, y2r, y2i);
-                    pb.ar = fma(t1[k + 3], y2r * t1[k + 9], fma(t1[k], y1r * t1[k + 8], u1));
-                    pb.ai = fma(t1[k + 3], y2i * t1[k + 9], t1[k] * (y1i * t1[k + 8]));
+                    step_only(t0 + k, len, u1, pa);
+                    step_only(t1 + k, len, u1, pb);
                 } else {
-                    sg = G.seg[s0 + 1];
+                    sg = load_seg<SEG_SMEM>(G, s0 + 1);
                     step_first(t0 + k, len, u1, u2, u3, pa);
                     step_first(t1 + k, len, u1, u2, u3, pb);
                     for (int s = s0 + 1; s < s1 - 1; ++s) {
                         const int km = sg.layer * ls;
                         const double lm = sg.len;
-                        sg = G.seg[s + 1];
+                        sg = load_seg<SEG_SMEM>(G, s + 1);
                         step_mid(t0 + km, lm, pa);
                         step_mid(t1 + km, lm, pb);
                     }
@@ -337,7 +343,9 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     double* msw = smem + (size_t)kEntry * T.n_layers * 2 * L.cb;   // [2 proc][2 what][2 parity][cbs]
     const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_layers, L.cb), L.seg_smem != 0);
     GlobalSink sink{osc_out + (size_t)g * 2 * nrow * T.n_etrue, osc_out + ((size_t)g * 2 + 1) * nrow * T.n_etrue, T.n_etrue};
-    osc_stage(T, G, p, i0, cb, L.cb, tbl, msw, p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr, sink, vcol, vdelta);
+    double* p1e = p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr;
+    if (L.seg_smem) osc_stage<true>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink, vcol, vdelta);
+    else osc_stage<false>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink, vcol, vdelta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -757,7 +765,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     double* p8s = smem + osc_smem_doubles(T.n_layers, cbs);
     double* phs = p8s + (size_t)rows * ldp;
     double* scr = p8s + fold_p_doubles(nT, nrow);
-    const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), L.seg_smem != 0);
+    const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), true);   // the host only launches this kernel when they fit
     fold_zero_padding(p8s, nT, nrow, ldp);
     const int n_osc = L.n_points / L.group;
     for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
@@ -770,7 +778,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
             // the table of the previous chunk is still being read by slower warps; the previous point's fold is
             // done with the probability tile once its closing barrier has been passed
             if (i0 > 0) __syncthreads();
-            osc_stage(T, G, po, i0, min(cbs, nT - i0), cbs, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
+            osc_stage<true>(T, G, po, i0, min(cbs, nT - i0), cbs, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
         }
         for (int q = 0; q < L.group; ++q) {
             const size_t b = (size_t)g * L.group + q;
