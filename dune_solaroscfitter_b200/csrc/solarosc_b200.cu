@@ -356,12 +356,11 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         if (const char* e = std::getenv("SOLAROSC_LLH_CHUNKS")) chunks = std::max(1, atoi(e));
         else
             while (chunks < T.n_etrue &&
-                   llh_smem_bytes(T.n_layers, (T.n_etrue + chunks - 1) / chunks, T.n_etrue, T.n_cosz, h->max_ereco) + h->seg_bytes > budget)
+                   llh_smem_bytes(T.n_layers, (T.n_etrue + chunks - 1) / chunks, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double)) > budget)
                 ++chunks;
         h->fused_cb = (T.n_etrue + chunks - 1) / chunks;
-        h->fused_smem = llh_smem_bytes(T.n_layers, h->fused_cb, T.n_etrue, T.n_cosz, h->max_ereco);
-        h->fused_seg = h->fused_smem + h->seg_bytes <= std::max(budget, h->fused_smem);
-        if (h->fused_seg) h->fused_smem += h->seg_bytes;
+        h->fused_smem = llh_smem_bytes(T.n_layers, h->fused_cb, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double));
+        h->fused_seg = true;
         if (const char* e = std::getenv("SOLAROSC_LLH_EXTRA_SMEM")) h->fused_smem += (size_t)atoi(e);   // diagnostics: force fewer CTAs per SM
         h->fused_ok = h->fused_seg && h->fused_smem <= per_cta_max;   // the fused kernel reads the path tables from shared memory
     }

@@ -133,7 +133,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
     const double f8 = p[3], fh = p[4];
 
     for (int k = threadIdx.x; k < P; k += blockDim.x) out_grad[b * P + k] = 0.0;
-    fold_zero_padding(p8s, nT, nrow, ldp);
+    fold_zero_padding(p8s, nT, rows, ldp);
     {   // stage the base probabilities, clear the adjoint tile
         const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
         int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;

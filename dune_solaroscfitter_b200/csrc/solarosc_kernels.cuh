@@ -96,16 +96,28 @@ __host__ __device__ inline int fold_ldp(int n_etrue) {
 }
 __host__ __device__ inline int fold_rows(int nrow) { return 8 * ((nrow + 7) / 8); }
 __host__ __device__ inline size_t fold_p_doubles(int n_etrue, int nrow) { return (size_t)2 * fold_rows(nrow) * fold_ldp(n_etrue); }
+// scratch of the fold: CC scale vectors [2][4 kt], additive constants and background sums [4][8 nt], then the
+// per-warp slots of the closing reduction (kWarps doubles + kWarps flag words)
+__host__ __device__ inline size_t fold_vec_doubles(int n_etrue, int max_ereco) {
+    return (size_t)2 * 4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8);
+}
 __host__ __device__ inline size_t fold_scratch_doubles(int n_etrue, int max_ereco) {
-    return (size_t)4 * 4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8) + 8;
+    return fold_vec_doubles(n_etrue, max_ereco) + kWarps + (kWarps + 1) / 2;
 }
 __host__ __device__ inline size_t rates_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
     return sizeof(double) * (fold_p_doubles(n_etrue, 1 + n_cosz) + fold_scratch_doubles(n_etrue, max_ereco));
 }
-// fused kernel: eigen table + MSW of one energy chunk (cb coarse bins), probability tile, scratch
-__host__ __device__ inline size_t llh_smem_bytes(int n_layers, int cb, int n_etrue, int n_cosz, int max_ereco) {
-    return sizeof(double) * (osc_smem_doubles(n_layers, cb) + fold_p_doubles(n_etrue, 1 + n_cosz) +
-                             fold_scratch_doubles(n_etrue, max_ereco));
+// Fused kernel: eigen table + MSW of one energy chunk (cb coarse bins), probability tile, scratch, path tables.
+// The probability tile holds exactly 1 + n_cosz rows per process; the last 8-row MMA tile of a process reads past
+// them into whatever follows (the other process, the scratch, the path tables) -- harmless, because an output row
+// of an MMA depends on the same row of A only and the epilogue drops rows >= 1 + n_cosz -- and `tail` pads the
+// allocation in the odd case that what follows is shorter than that overrun.
+__host__ __device__ inline size_t llh_smem_bytes(int n_layers, int cb, int n_etrue, int n_cosz, int max_ereco, size_t seg_doubles) {
+    const int nrow = 1 + n_cosz, ldp = fold_ldp(n_etrue);
+    const size_t over = (size_t)(fold_rows(nrow) - nrow) * ldp, after = fold_scratch_doubles(n_etrue, max_ereco) + seg_doubles;
+    const size_t tail = over > after ? over - after : 0;
+    return sizeof(double) * (osc_smem_doubles(n_layers, cb) + (size_t)2 * nrow * ldp + fold_scratch_doubles(n_etrue, max_ereco) +
+                             seg_doubles + tail);
 }
 
 // Oscillation-stage directions of the gradient path: sin2_th12, sin2_th13, dm2_21, then earth_norm_k.
@@ -466,7 +478,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
     const double f8 = p[3], fh = p[4];
     const double* pd = p + D.param_off;
     double* scale = scr;
-    double* cst_es = scr + 16 * kt;
+    double* cst_es = scr + 8 * kt;
     double* cst_cc = cst_es + 8 * nte;
     double* bgs_es = cst_cc + 8 * ntc;
     double* bgs_cc = bgs_es + 8 * nte;
@@ -478,8 +490,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
             const double l = D.log_e_norm[i];
             sh = exp(fma(p[6], l, p[7] * (l * l))) * p[5];
         }
-        scale[i] = f8; scale[4 * kt + i] = fh;
-        scale[8 * kt + i] = f8 * sh; scale[12 * kt + i] = fh * sh;
+        scale[i] = f8 * sh; scale[4 * kt + i] = fh * sh;
     }
     for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
         double acc = 0.0, c = 0.0;
@@ -513,16 +524,19 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
 template <int MODE>
 __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
                                            const double* p8s, const double* phs, int ldp, double* scr,
-                                           const RatesOut& O, double* red, uint32_t* redf, bool vectors_ready = false) {
+                                           const RatesOut& O, bool vectors_ready = false) {
     // vectors_ready: fold_vectors of detector 0 already ran for this point (the fused kernel does it next to the
     // eigen table, where its load and exp latencies hide behind other warps' work)
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fg = lane >> 2, ft = lane & 3;
-    // scale vectors of the B fragments, [4*kt] each: ES 8B (F8), ES hep (Fh), CC 8B (F8 s_i), CC hep (Fh s_i)
+    // scale vectors of the CC B fragments, [4*kt] each: 8B (F8 s_i), hep (Fh s_i); ES scales by F8 / Fh alone
     double* scale = scr;
-    double* cst_es = scr + 16 * kt;          // per reco bin additive constants
+    double* cst_es = scr + 8 * kt;           // per reco bin additive constants
+    double* red = scr + fold_vec_doubles(nT, L.max_ereco);
+    uint32_t* redf = reinterpret_cast<uint32_t*>(red + kWarps);
+    const double f8 = p[3], fh = p[4];
     // earth-norm bounds (reference likelihood_debug.jl:1-4, likelihood_builder.jl:227)
     bool oob = false;
     if (T.earth_unc)
@@ -578,7 +592,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
             const bool v0 = j0 < nR, v1 = j0 + 1 < nR;
             const double* m8 = (kThr ? (is_es ? D.a8_thr : D.b8_thr) : (is_es ? D.a8 : D.b8)) + ft * ldb + n0 + fg;   // B fragment of k-step 0
             const double* mh = (kThr ? (is_es ? D.ah_thr : D.bh_thr) : (is_es ? D.ah : D.bh)) + ft * ldb + n0 + fg;
-            const uint32_t sc8 = smem_addr(scale + (is_es ? 0 : 8 * kt) + ft), sch = sc8 + 4u * kt * 8u;
+            const uint32_t sc8 = smem_addr(scale + ft), sch = sc8 + 4u * kt * 8u;
             const double c0 = v0 ? (is_es ? cst_es : cst_cc)[j0] : 0.0, c1 = v1 ? (is_es ? cst_es : cst_cc)[j0 + 1] : 0.0;
             const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
             const double* obs = is_es ? D.obs_es : D.obs_cc;
@@ -599,7 +613,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
                 double b8n = __ldg(m8), bhn = __ldg(mh);
                 const double *q8 = m8, *qh = mh;
                 for (int ks = 0; ks < kt; ++ks) {
-                    const double b8v = b8n * lds_f64(sc8 + 32u * ks), bhv = bhn * lds_f64(sch + 32u * ks);
+                    const double b8v = b8n * (is_es ? f8 : lds_f64(sc8 + 32u * ks)), bhv = bhn * (is_es ? fh : lds_f64(sch + 32u * ks));
                     if (ks + 1 < kt) { q8 += bstep; qh += bstep; b8n = __ldg(q8); bhn = __ldg(qh); }
 #pragma unroll
                     for (int c = 0; c < kMC; ++c) {
@@ -711,10 +725,10 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
 // Zero the K padding of the probability tile (columns n_etrue .. 4*ceil(n_etrue/4) - 1 of both processes): the fold
 // multiplies them by the zero rows of the constant matrices, so they must be finite.  Padding ROWS need nothing:
 // an output row of an MMA only depends on the same row of A, and the epilogue drops rows >= nrow.
-__device__ __forceinline__ void fold_zero_padding(double* ps, int nT, int nrow, int ldp) {
-    const int rows = fold_rows(nrow), padc = 4 * fold_kt(nT) - nT;
+__device__ __forceinline__ void fold_zero_padding(double* ps, int nT, int rows_alloc, int ldp) {
+    const int padc = 4 * fold_kt(nT) - nT;   // rows_alloc: rows per process as laid out by the caller
     if (padc == 0) return;
-    for (int t = threadIdx.x; t < 2 * rows * padc; t += blockDim.x) {
+    for (int t = threadIdx.x; t < 2 * rows_alloc * padc; t += blockDim.x) {
         const int r = t / padc, c = t - r * padc;
         ps[(size_t)r * ldp + nT + c] = 0.0;
     }
@@ -725,15 +739,13 @@ __global__ void __launch_bounds__(kThreads, SOLAROSC_RATES_MINBLOCKS)
 rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params,
              const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[kWarps];
-    __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
     double* p8s = smem;
     double* phs = p8s + (size_t)rows * ldp;
     double* scr = p8s + fold_p_doubles(nT, nrow);
     const size_t b = blockIdx.x;
     const double* src = osc + (b / L.group) * 2 * nrow * nT;
-    fold_zero_padding(p8s, nT, nrow, ldp);
+    fold_zero_padding(p8s, nT, rows, ldp);
     {   // stage the probabilities: (row, i) advance by blockDim.x without a division in the loop
         const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
         int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;
@@ -744,7 +756,7 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
             if (i >= nT) { i -= nT; ++row; }
         }
     }
-    fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf);
+    fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O);
 }
 
 // Persistent fused kernel: every CTA walks oscillation points g = blockIdx.x, blockIdx.x + gridDim.x, ...  Per
@@ -755,16 +767,14 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, SOLAROSC_LLH_MINBLOCKS)
 llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params, RatesOut O) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[kWarps];
-    __shared__ uint32_t redf[kWarps];
-    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT);
     SOLAROSC_PH(0);
     const int cbs = L.osc_cb;
     double* tbl = smem;
     double* msw = smem + (size_t)kEntry * T.n_layers * 2 * cbs;
-    double* p8s = smem + osc_smem_doubles(T.n_layers, cbs);
-    double* phs = p8s + (size_t)rows * ldp;
-    double* scr = p8s + fold_p_doubles(nT, nrow);
+    double* p8s = smem + osc_smem_doubles(T.n_layers, cbs);   // [nrow][ldp] per process, no padding rows (llh_smem_bytes)
+    double* phs = p8s + (size_t)nrow * ldp;
+    double* scr = phs + (size_t)nrow * ldp;
     const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), true);   // the host only launches this kernel when they fit
     fold_zero_padding(p8s, nT, nrow, ldp);
     const int n_osc = L.n_points / L.group;
@@ -783,7 +793,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
         for (int q = 0; q < L.group; ++q) {
             const size_t b = (size_t)g * L.group + q;
             // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
-            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, red, redf, q == 0);
+            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, q == 0);
         }
     }
 }
