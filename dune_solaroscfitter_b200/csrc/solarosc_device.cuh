@@ -16,6 +16,7 @@ namespace solarosc {
 
 constexpr double kGF = 5.4489e-5;                 // reference osc.jl:51
 constexpr double kPhase = 2.5338653580781976;     // reference osc.jl:361
+constexpr double kPhaseQT = kPhase * 0.63661977236758134308;   // the same rate in quarter turns (x 2/pi)
 constexpr double kDm31 = 2.5e-3;                  // reference osc.jl:44 (theta23, deltaCP drop out of P1e)
 constexpr int kMaxDet = 4;
 
@@ -76,8 +77,17 @@ struct DevTables {
         -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,         \
         -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,         \
         2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, 0.0
-static __constant__ double kTrigDev[16] = {SOLAROSC_TRIG_TABLE};
-static const double kTrigHost[16] = {SOLAROSC_TRIG_TABLE};
+// Quarter-turn kernels of sincos_qt (tools/fit_quarter_turn_trig.py, Remez in 60-digit arithmetic): for |f| <= 1/2
+//   sin(pi/2 f) = f (S0 + z S1 + ... + z^5 S5),  cos(pi/2 f) = 1 + z (C0 + z C1 + ... + z^5 C5),  z = f^2,
+// absolute errors 3.4e-15 and 3.3e-16 evaluated in double -- three orders of magnitude below the 1e-11 rad
+// rounding noise that phases of up to 7e4 rad carry anyway.
+#define SOLAROSC_QT_TABLE                                                                             \
+    1.57079632679488989666e+00, -6.45964097504311052234e-01, 7.96926261558089099601e-02,              \
+        -4.68175259216174061150e-03, 1.60429268258354377910e-04, -3.55639139782485082505e-06,         \
+        -1.23370055013616908290e+00, 2.53669507900830593083e-01, -2.08634807532030522315e-02,         \
+        9.19260101511700715264e-04, -2.52007040774374478794e-05, 4.66321043146625407711e-07
+static __constant__ double kTrigDev[28] = {SOLAROSC_TRIG_TABLE, SOLAROSC_QT_TABLE};
+static const double kTrigHost[28] = {SOLAROSC_TRIG_TABLE, SOLAROSC_QT_TABLE};
 
 #if defined(__CUDA_ARCH__)
 #define SOLAROSC_HD __host__ __device__ __forceinline__
@@ -140,6 +150,37 @@ SOLAROSC_HD void sincos_phase(double x, double& s, double& c) {
     const double ss = (q & 1) ? cr : sr;
     const double cc = (q & 1) ? sr : cr;
     s = flip_sign(ss, q << 30);          // bit 1 of q -> sign bit
+    c = flip_sign(cc, (q + 1) << 30);
+}
+
+// sin/cos of the phase len * kq measured in QUARTER TURNS (kq = rate in quarter turns per km, tabulated per
+// eigen entry): the product, its rounding to an integer number of quarter turns and the reduced argument all
+// come out of two FMAs on the unrounded product -- f = len*kq - round(len*kq) is formed from the exact 106-bit
+// product, so the reduction adds no error at all -- and the minimax kernels take f directly (the pi/2 lives in
+// their coefficients).  16 FP64 instructions for phase product + sine + cosine, against 1 + 20 with
+// sincos_phase.  |len * kq| < 2^31.
+SOLAROSC_HD void sincos_qt(double len, double kq, double& s, double& c) {
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(len, kq, kMagic);
+    const int q = lo_int(t);
+    const double f = fma(len, kq, -(t - kMagic));
+    const double z = f * f;
+    double ps = fma(z, SOLAROSC_TRIG(21), SOLAROSC_TRIG(20));
+    ps = fma(z, ps, SOLAROSC_TRIG(19));
+    ps = fma(z, ps, SOLAROSC_TRIG(18));
+    ps = fma(z, ps, SOLAROSC_TRIG(17));
+    ps = fma(z, ps, SOLAROSC_TRIG(16));
+    const double sr = f * ps;
+    double pc = fma(z, SOLAROSC_TRIG(27), SOLAROSC_TRIG(26));
+    pc = fma(z, pc, SOLAROSC_TRIG(25));
+    pc = fma(z, pc, SOLAROSC_TRIG(24));
+    pc = fma(z, pc, SOLAROSC_TRIG(23));
+    pc = fma(z, pc, SOLAROSC_TRIG(22));
+    const double cr = fma(z, pc, 1.0);
+    // quadrant q mod 4: 0 (sr, cr)   1 (cr, -sr)   2 (-sr, -cr)   3 (-cr, sr)
+    const double ss = (q & 1) ? cr : sr;
+    const double cc = (q & 1) ? sr : cr;
+    s = flip_sign(ss, q << 30);
     c = flip_sign(cc, (q + 1) << 30);
 }
 
@@ -229,6 +270,7 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
 // so q_0 and the common phase are never needed (reference osc_kernel, osc.jl:360-364, applied to a
 // vector instead of forming the 3x3 products of osc.jl:442).
 //   [0..2] q_1   [3..5] q_2   [6] c*(mu_1-mu_0)/E   [7] c*(mu_2-mu_0)/E   [8] q_1.u   [9] q_2.u
+// with c = 2.5338653580781976 * 2/pi: the phase rates are kept in quarter turns per km (sincos_qt).
 // Ten doubles = 80 bytes: entries are 16-byte aligned, so a step fetches its eight numbers with four 128-bit
 // loads, and the 80-byte pitch between the entries of consecutive energies (the lanes of a warp) keeps every
 // quarter-warp of such a load on distinct banks.
@@ -238,7 +280,7 @@ constexpr int kEntry = 10;
 SOLAROSC_HD void make_entry(double dm21, double a, double e_gev, double u1, double u2, double u3, double* ent) {
     double q[9], w2, w3;
     eig_rank_one(dm21, kDm31, a, u1, u2, u3, q, w2, w3);
-    const double f = kPhase / e_gev;   // phase = 2.5338653580781976 * (l/e) * lambda  (osc.jl:361)
+    const double f = kPhaseQT / e_gev;   // phase = 2.5338653580781976 * (l/e) * lambda  (osc.jl:361), in quarter turns
     ent[0] = q[1]; ent[1] = q[4]; ent[2] = q[7];
     ent[3] = q[2]; ent[4] = q[5]; ent[5] = q[8];
     ent[6] = f * w2; ent[7] = f * w3;
@@ -258,21 +300,19 @@ SOLAROSC_HD Ent load_ent(const double* e) {
     return Ent{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 }
 
-// y_n = e^{-i phi_n} - 1 for both excited eigenstates of this entry
-SOLAROSC_HD void step_phases(const Ent& e, double len, double& y1r, double& y1i, double& y2r, double& y2i) {
-    double s1, c1, s2, c2;
-    sincos_phase(len * e.k1, s1, c1);
-    sincos_phase(len * e.k2, s2, c2);
-    y1r = c1 - 1.0; y1i = -s1; y2r = c2 - 1.0; y2i = -s2;
+// e^{-i phi_n} = c_n - i s_n for both excited eigenstates of this entry
+SOLAROSC_HD void step_phases(const Ent& e, double len, double& s1, double& c1, double& s2, double& c2) {
+    sincos_qt(len, e.k1, s1, c1);
+    sincos_qt(len, e.k2, s2, c2);
 }
 
-// first step of a path: psi = u is real, q_n.u is tabulated
+// first step of a path: psi = u is real, q_n.u is tabulated; t_n = (e^{-i phi_n} - 1) (q_n.u)
 SOLAROSC_HD void step_first(const double* ep, double len, double u1, double u2, double u3, State& p) {
     const Ent e = load_ent(ep);
     const double2 d = reinterpret_cast<const double2*>(ep)[4];
-    double y1r, y1i, y2r, y2i;
-    step_phases(e, len, y1r, y1i, y2r, y2i);
-    const double t1r = y1r * d.x, t1i = y1i * d.x, t2r = y2r * d.y, t2i = y2i * d.y;
+    double s1, c1, s2, c2;
+    step_phases(e, len, s1, c1, s2, c2);
+    const double t1r = fma(c1, d.x, -d.x), t1i = -s1 * d.x, t2r = fma(c2, d.y, -d.y), t2i = -s2 * d.y;
     p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, u1)); p.ai = fma(e.q2x, t2i, e.q1x * t1i);
     p.br = fma(e.q2y, t2r, fma(e.q1y, t1r, u2)); p.bi = fma(e.q2y, t2i, e.q1y * t1i);
     p.cr = fma(e.q2z, t2r, fma(e.q1z, t1r, u3)); p.ci = fma(e.q2z, t2i, e.q1z * t1i);
@@ -282,20 +322,20 @@ SOLAROSC_HD void step_first(const double* ep, double len, double u1, double u2, 
 SOLAROSC_HD void step_only(const double* ep, double len, double u1, State& p) {
     const Ent e = load_ent(ep);
     const double2 d = reinterpret_cast<const double2*>(ep)[4];
-    double y1r, y1i, y2r, y2i;
-    step_phases(e, len, y1r, y1i, y2r, y2i);
-    p.ar = fma(e.q2x, y2r * d.y, fma(e.q1x, y1r * d.x, u1));
-    p.ai = fma(e.q2x, y2i * d.y, e.q1x * (y1i * d.x));
+    double s1, c1, s2, c2;
+    step_phases(e, len, s1, c1, s2, c2);
+    p.ar = fma(e.q2x, fma(c2, d.y, -d.y), fma(e.q1x, fma(c1, d.x, -d.x), u1));
+    p.ai = -fma(e.q2x, s2 * d.y, e.q1x * (s1 * d.x));
 }
 
-// t_n = y_n * (q_n . psi)
+// t_n = (e^{-i phi_n} - 1) (q_n . psi), formed as c w + s (-i w) - w without ever forming e^{-i phi} - 1
 SOLAROSC_HD void step_project(const Ent& e, double len, const State& p, double& t1r, double& t1i, double& t2r, double& t2i) {
-    double y1r, y1i, y2r, y2i;
-    step_phases(e, len, y1r, y1i, y2r, y2i);
+    double s1, c1, s2, c2;
+    step_phases(e, len, s1, c1, s2, c2);
     const double w1r = fma(e.q1z, p.cr, fma(e.q1y, p.br, e.q1x * p.ar)), w1i = fma(e.q1z, p.ci, fma(e.q1y, p.bi, e.q1x * p.ai));
     const double w2r = fma(e.q2z, p.cr, fma(e.q2y, p.br, e.q2x * p.ar)), w2i = fma(e.q2z, p.ci, fma(e.q2y, p.bi, e.q2x * p.ai));
-    t1r = fma(-y1i, w1i, y1r * w1r); t1i = fma(y1i, w1r, y1r * w1i);
-    t2r = fma(-y2i, w2i, y2r * w2r); t2i = fma(y2i, w2r, y2r * w2i);
+    t1r = fma(c1, w1r, fma(s1, w1i, -w1r)); t1i = fma(c1, w1i, fma(-s1, w1r, -w1i));
+    t2r = fma(c2, w2r, fma(s2, w2i, -w2r)); t2i = fma(c2, w2i, fma(-s2, w2r, -w2i));
 }
 
 SOLAROSC_HD void step_mid(const double* ep, double len, State& p) {

@@ -13,6 +13,11 @@ void hm_sincos(const double* x, int n, double* s, double* c) {
     for (int i = 0; i < n; ++i) sincos_phase(x[i], s[i], c[i]);
 }
 
+// sine and cosine of len[i] * kq[i] quarter turns (the layer step's phase factor)
+void hm_sincos_qt(const double* len, const double* kq, int n, double* s, double* c) {
+    for (int i = 0; i < n; ++i) sincos_qt(len[i], kq[i], s[i], c[i]);
+}
+
 void hm_eig(double d21, double d31, double a, double u1, double u2, double u3, double* q, double* w) {
     eig_rank_one(d21, d31, a, u1, u2, u3, q, w[0], w[1]);
 }

@@ -29,6 +29,7 @@ def hm():
                         "-shared", "-o", OUT, SRC], check=True, capture_output=True)
     L = C.CDLL(OUT)
     L.hm_sincos.argtypes = [dp, C.c_int, dp, dp]
+    L.hm_sincos_qt.argtypes = [dp, dp, C.c_int, dp, dp]
     L.hm_eig.argtypes = [C.c_double] * 6 + [dp, dp]
     L.hm_p1e.argtypes = [dp, C.c_int, ip, ip, dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, dp]
     L.hm_msw_c2m.argtypes = [C.c_double] * 5
@@ -44,6 +45,26 @@ def test_sincos_phase_accuracy(hm):
     hm.hm_sincos(x.ctypes.data_as(dp), len(x), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
     assert np.max(np.abs(s - np.sin(x))) < 4e-16
     assert np.max(np.abs(c - np.cos(x))) < 4e-16
+
+
+def test_sincos_quarter_turns_accuracy(hm):
+    """sincos_qt reduces the exact product len * kq, so the reference reduces it exactly too (rationals)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(1)
+    n = 20000
+    ln = np.concatenate([rng.uniform(1.0, 1.3e4, n), [0.0, 1.0, 2.0, 12742.0, 1.0, 3.0]])
+    kq = np.concatenate([rng.uniform(0.0, 4.0, n // 2), rng.uniform(0.0, 1e-3, n - n // 2), [1.0, 0.5, 0.25, 3.5, 1e-300, 0.5]])
+    ref_s, ref_c = np.empty_like(ln), np.empty_like(ln)
+    for i in range(len(ln)):
+        x = Fraction(float(ln[i])) * Fraction(float(kq[i]))
+        k = round(x)
+        f = float(x - k) * (math.pi / 2)
+        sr, cr = math.sin(f), math.cos(f)
+        ref_s[i], ref_c[i] = [(sr, cr), (cr, -sr), (-sr, -cr), (-cr, sr)][k % 4]
+    s, c = np.empty_like(ln), np.empty_like(ln)
+    hm.hm_sincos_qt(ln.ctypes.data_as(dp), kq.ctypes.data_as(dp), len(ln), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    # degree-11 minimax sine kernel: 3.4e-15; it serves as the cosine in odd quadrants
+    assert np.max(np.abs(s - ref_s)) < 5e-15 and np.max(np.abs(c - ref_c)) < 5e-15
 
 
 def _eig(hm, d21, d31, a, u):
