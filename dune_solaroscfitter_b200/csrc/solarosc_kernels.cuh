@@ -262,6 +262,9 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
             }
         }
     }
+    // work counter of phase 2 (its previous readers all left their loop before the barrier that ended the last call)
+    __shared__ int s_next;
+    if (threadIdx.x == 0) s_next = 0;
     SOLAROSC_PH(2);
     __syncthreads();
     SOLAROSC_PH(3);
@@ -273,14 +276,21 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
 
     // ---- phase 2: Earth propagation, one item = (coarse zenith row, coarse energy bin) -----------
     // Lanes of a warp walk the same path at neighbouring energies, so the layer loop is warp-uniform.
-    // Rows are visited longest-first and the passes alternate direction (thread t takes item t of even
-    // passes and item nthreads-1-t of odd ones), so every thread gets the same mix of long and short paths.
+    // Rows are listed longest path first and every warp draws its next 32 items from a shared counter when it is
+    // done with the previous ones (longest-processing-time-first): the warps of a CTA reach the closing barrier
+    // within one short path of each other.  The next draw is issued before the current items are computed.
     const double inv_block = 1.0 / (2.0 * T.n_sub);
     const int n_items = T.n_cosz * cb;
     const double inv_cb = 1.0 / cb;
     const int ls = 2 * cbs * kEntry;                            // doubles between consecutive layers
-    for (int base = 0, pass = 0; base < n_items; base += blockDim.x, ++pass) {
-        const int item = base + ((pass & 1) ? (int)blockDim.x - 1 - (int)threadIdx.x : (int)threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    int drawn = 0;
+    if (lane == 0) drawn = atomicAdd(&s_next, 1);
+    for (;;) {
+        const int wi = __shfl_sync(0xffffffffu, drawn, 0);
+        if (wi * 32 >= n_items) break;
+        if (lane == 0) drawn = atomicAdd(&s_next, 1);
+        const int item = wi * 32 + lane;
         if (item >= n_items) continue;
         const int zr = (int)((item + 0.5) * inv_cb), j = item - zr * cb;   // exact: item < 2^31, cb >= 1
         double acc8 = 0.0, acch = 0.0;
