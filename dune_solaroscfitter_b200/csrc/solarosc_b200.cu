@@ -290,6 +290,28 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
             D.ah_thr = h->upload_vec(shifted(ah, le, D.n_es, D.index_es - 1, D.nte_thr));
             D.b8_thr = h->upload_vec(shifted(b8, lc, D.n_cc, D.index_cc - 1, D.ntc_thr));
             D.bh_thr = h->upload_vec(shifted(bh, lc, D.n_cc, D.index_cc - 1, D.ntc_thr));
+            // Work list of the likelihood fold (fold_stage): per column block, groups of kMCa row tiles, then the
+            // remaining tiles in groups of kMCb; longest item first, each to the warp with the least work so far.
+            {
+                const int mt = (1 + T.n_cosz + 7) / 8, nb = D.nte_thr + D.ntc_thr;
+                const int na = mt / kMCa, nbm = (mt - kMCa * na + kMCb - 1) / kMCb;
+                const int ntask = nb * (na + nbm);
+                D.fold_ntask = 0;
+                if (ntask <= kMaxFoldTasks) {
+                    int load[kWarps] = {0};
+                    for (int t = 0; t < ntask; ++t) {
+                        const bool big = t < nb * na;
+                        const int col = (big ? t : t - nb * na) % nb;
+                        const bool on = col < D.nte_thr ? D.es_mode != 0 : D.cc_mode != 0;
+                        int w = 0;
+                        for (int x = 1; x < kWarps; ++x)
+                            if (load[x] < load[w]) w = x;
+                        D.fold_owner[t] = (unsigned char)w;
+                        if (on) load[w] += big ? kMCa : kMCb;
+                    }
+                    D.fold_ntask = ntask;
+                }
+            }
         }
         D.raw_bg_es = h->upload(s.raw_bg_es, (size_t)D.n_bg_es * D.n_es);
         D.raw_bg_cc = h->upload(s.raw_bg_cc, (size_t)D.n_bg_cc * D.n_cc);

@@ -19,6 +19,7 @@ constexpr double kPhase = 2.5338653580781976;     // reference osc.jl:361
 constexpr double kPhaseQT = kPhase * 0.63661977236758134308;   // the same rate in quarter turns (x 2/pi)
 constexpr double kDm31 = 2.5e-3;                  // reference osc.jl:44 (theta23, deltaCP drop out of P1e)
 constexpr int kMaxDet = 4;
+constexpr int kMaxFoldTasks = 48;
 
 // one applied layer step: 0-based layer and length [km]; 16 bytes so a step's metadata is one load
 struct __align__(16) Seg {
@@ -36,6 +37,10 @@ struct DevDetector {
     // the same matrices with the columns below the likelihood threshold removed: column j' is reco bin index_xx - 1 + j'
     const double *a8_thr, *ah_thr, *b8_thr, *bh_thr;
     int nte_thr, ntc_thr;                 // their widths in 8-column blocks
+    // likelihood fold: warp that runs work item t (fold_stage; longest-first assignment made at create);
+    // fold_ntask = 0 when the list does not fit, the kernel then deals the items round-robin
+    int fold_ntask;
+    unsigned char fold_owner[kMaxFoldTasks];
     const double *raw_bg_es, *raw_bg_cc;  // [n_bg][n_ereco]
     double bg_es_area[SOLAROSC_MAX_BG];   // face area per ES component (0 => not scaled by a nuisance)
     int bg_cc_norm[SOLAROSC_MAX_BG];      // index of the CC nuisance scaling component i, -1 => fixed

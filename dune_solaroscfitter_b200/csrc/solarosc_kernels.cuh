@@ -34,7 +34,12 @@ namespace solarosc {
 #endif
 constexpr int kThreads = SOLAROSC_OSC_THREADS;   // every kernel here uses this block size
 constexpr int kWarps = kThreads / 32;
-constexpr int kMC = 7;   // row tiles of the fold a warp keeps in flight (51 rows = 7 tiles in the default binning)
+constexpr int kMC = 7;   // row tiles a fold keeps in flight (51 rows = 7 tiles in the default binning)
+#ifndef SOLAROSC_FOLD_MCA
+#define SOLAROSC_FOLD_MCA 5
+#define SOLAROSC_FOLD_MCB 2
+#endif
+constexpr int kMCa = SOLAROSC_FOLD_MCA, kMCb = SOLAROSC_FOLD_MCB;   // grouped evaluation: finer work items (fold_stage)   // row tiles per work item of the forward fold: groups of kMCa, remainder in groups of kMCb
 
 struct OscLaunch {
     int n_points;     // oscillation points in this launch
@@ -531,6 +536,122 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
     }
 }
 
+// One work item of the fold: column block `col` (ES blocks first, then CC) against NT consecutive row tiles
+// starting at tile m0, all NT accumulator tiles in flight, epilogue on the accumulator registers.
+template <int MODE>
+struct FoldTask {
+    const DevTables& T;
+    const RatesLaunch& L;
+    const DevDetector& D;
+    const RatesOut& O;
+    const double *p8s, *phs, *scale, *cst_es, *cst_cc;
+    double f8, fh;
+    size_t b;
+    int ldp, nrow, mt, kt, bte, btc;
+    bool oob;
+
+    template <int NT>
+    __device__ __forceinline__ void run(int col, int m0, double& part, uint32_t& fl, double& d_es, double& n_es, double& d_cc,
+                                        double& n_cc) const {
+        constexpr bool kThr = MODE == kModeLlh || MODE == kModeAsym;
+        const int lane = threadIdx.x & 31, fg = lane >> 2, ft = lane & 3;
+        const int nZ = nrow - 1;
+        const bool is_es = col < bte;
+        const int n0 = 8 * (is_es ? col : col - bte);
+        const int ldb = 8 * (is_es ? bte : btc);
+        const int nR = is_es ? D.n_es : D.n_cc;
+        const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
+        const int j0 = (kThr ? idx0 : 0) + n0 + 2 * ft;                  // this lane's two reco bins
+        const bool v0 = j0 < nR, v1 = j0 + 1 < nR;
+        const double* m8 = (kThr ? (is_es ? D.a8_thr : D.b8_thr) : (is_es ? D.a8 : D.b8)) + ft * ldb + n0 + fg;   // B fragment of k-step 0
+        const double* mh = (kThr ? (is_es ? D.ah_thr : D.bh_thr) : (is_es ? D.ah : D.bh)) + ft * ldb + n0 + fg;
+        const uint32_t sc8 = smem_addr(scale + ft), sch = sc8 + 4u * kt * 8u;
+        const double c0 = v0 ? (is_es ? cst_es : cst_cc)[j0] : 0.0, c1 = v1 ? (is_es ? cst_es : cst_cc)[j0 + 1] : 0.0;
+        const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
+        const double* obs = is_es ? D.obs_es : D.obs_cc;
+        double* day = is_es ? O.es_day : O.cc_day;
+        double* night = is_es ? O.es_night : O.cc_night;
+        const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
+        const size_t bstep = (size_t)4 * ldb;
+        const uint32_t tile_bytes = 8u * (uint32_t)ldp * 8u;   // one 8-row tile of the probability tile
+        double acc[NT][2];
+        uint32_t a8[NT];   // shared-memory address of this lane's A element of k-step 0, per row tile
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {
+            acc[c][0] = c0; acc[c][1] = c1;
+            // tiles past the end repeat the last one: their results are dropped in the epilogue
+            a8[c] = smem_addr(p8s + fg * ldp + ft) + (uint32_t)min(m0 + c, mt - 1) * tile_bytes;
+        }
+        const uint32_t dproc = smem_addr(phs) - smem_addr(p8s);
+        double b8n = __ldg(m8), bhn = __ldg(mh);
+        const double *q8 = m8, *qh = mh;
+        for (int ks = 0; ks < kt; ++ks) {
+            const double b8v = b8n * (is_es ? f8 : lds_f64(sc8 + 32u * ks)), bhv = bhn * (is_es ? fh : lds_f64(sch + 32u * ks));
+            if (ks + 1 < kt) { q8 += bstep; qh += bstep; b8n = __ldg(q8); bhn = __ldg(qh); }
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + 32u * ks), b8v);
+                dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + dproc + 32u * ks), bhv);
+            }
+        }
+        // ---- epilogue on the accumulator registers ----------------------------------------------
+        double r[NT][2];
+        bool vr[NT];
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {
+            const int row = 8 * (m0 + c) + fg;
+            vr[c] = m0 + c < mt && row < nrow;
+            const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
+            r[c][0] = w * acc[c][0];
+            r[c][1] = w * acc[c][1];
+        }
+        if (MODE == kModeLlh) {
+            double2 o0[NT], o1[NT];
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const int row = 8 * (m0 + c) + fg;
+                o0[c] = (vr[c] && v0) ? __ldg(ol + row * nR + j0) : make_double2(0.0, 0.0);
+                o1[c] = (vr[c] && v1) ? __ldg(ol + row * nR + j0 + 1) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const double t0 = poisson_term((vr[c] && v0) ? r[c][0] : 1.0, o0[c].x, o0[c].y, fl);
+                const double t1 = poisson_term((vr[c] && v1) ? r[c][1] : 1.0, o1[c].x, o1[c].y, fl);
+                part += ((vr[c] && v0) ? t0 : 0.0) + ((vr[c] && v1) ? t1 : 0.0);
+            }
+        } else if (MODE == kModeAsym) {
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                const double s01 = ((vr[c] && v0) ? r[c][0] : 0.0) + ((vr[c] && v1) ? r[c][1] : 0.0);
+                const bool is_day = m0 + c == 0 && fg == 0;
+                if (is_es) { if (is_day) d_es += s01; else n_es += s01; }
+                else { if (is_day) d_cc += s01; else n_cc += s01; }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                if (!vr[c]) continue;
+                const int row = 8 * (m0 + c) + fg;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jx = j0 + h;
+                    if (jx >= nR) continue;
+                    double v = r[c][h];
+                    if (MODE == kModePerbin) {
+                        v = (jx >= idx0 && jx < nR - 1) ? perbin_term(v, obs[row * nR + jx]) : 0.0;
+                        if (oob) v = -INFINITY;
+                    }
+                    if (row == 0) {
+                        if (day) day[b * nR + jx] = v;
+                    } else if (night) {
+                        night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = v;
+                    }
+                }
+            }
+        }
+    }
+};
+
 template <int MODE>
 __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
                                            const double* p8s, const double* phs, int ldp, double* scr,
@@ -540,7 +661,6 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int fg = lane >> 2, ft = lane & 3;
     // scale vectors of the CC B fragments, [4*kt] each: 8B (F8 s_i), hep (Fh s_i); ES scales by F8 / Fh alone
     double* scale = scr;
     double* cst_es = scr + 8 * kt;           // per reco bin additive constants
@@ -585,107 +705,36 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         SOLAROSC_PH(7);
         double part = 0.0;
         double d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;   // asymmetry mode: day / night totals above threshold
-        const uint32_t tile_bytes = 8u * (uint32_t)ldp * 8u;   // one 8-row tile of the probability tile
         // likelihood and asymmetry only look at the bins from the threshold on (likelihood_builder.jl:5-20,129-144):
         // they use the copies of the fold matrices whose columns start at the threshold bin, so no column block is
         // spent on bins that never enter the sum (24 bins = 3 blocks instead of 4 per channel in the default binning)
         constexpr bool kThr = MODE == kModeLlh || MODE == kModeAsym;
         const int bte = kThr ? D.nte_thr : nte, btc = kThr ? D.ntc_thr : ntc;
-        for (int task = warp; task < bte + btc; task += kWarps) {
-            const bool is_es = task < bte;
-            if (is_es ? !D.es_mode : !D.cc_mode) continue;
-            const int n0 = 8 * (is_es ? task : task - bte);
-            const int ldb = 8 * (is_es ? bte : btc);
-            const int nR = is_es ? D.n_es : D.n_cc;
-            const int idx0 = (is_es ? D.index_es : D.index_cc) - 1;
-            const int j0 = (kThr ? idx0 : 0) + n0 + 2 * ft;                  // this lane's two reco bins
-            const bool v0 = j0 < nR, v1 = j0 + 1 < nR;
-            const double* m8 = (kThr ? (is_es ? D.a8_thr : D.b8_thr) : (is_es ? D.a8 : D.b8)) + ft * ldb + n0 + fg;   // B fragment of k-step 0
-            const double* mh = (kThr ? (is_es ? D.ah_thr : D.bh_thr) : (is_es ? D.ah : D.bh)) + ft * ldb + n0 + fg;
-            const uint32_t sc8 = smem_addr(scale + ft), sch = sc8 + 4u * kt * 8u;
-            const double c0 = v0 ? (is_es ? cst_es : cst_cc)[j0] : 0.0, c1 = v1 ? (is_es ? cst_es : cst_cc)[j0 + 1] : 0.0;
-            const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
-            const double* obs = is_es ? D.obs_es : D.obs_cc;
-            double* day = is_es ? O.es_day : O.cc_day;
-            double* night = is_es ? O.es_night : O.cc_night;
-            const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
-            const size_t bstep = (size_t)4 * ldb;
-            for (int m0 = 0; m0 < mt; m0 += kMC) {
-                double acc[kMC][2];
-                uint32_t a8[kMC];   // shared-memory address of this lane's A element of k-step 0, per row tile
-#pragma unroll
-                for (int c = 0; c < kMC; ++c) {
-                    acc[c][0] = c0; acc[c][1] = c1;
-                    // tiles past the end repeat the last one: their results are dropped in the epilogue
-                    a8[c] = smem_addr(p8s + fg * ldp + ft) + (uint32_t)min(m0 + c, mt - 1) * tile_bytes;
-                }
-                const uint32_t dproc = smem_addr(phs) - smem_addr(p8s);
-                double b8n = __ldg(m8), bhn = __ldg(mh);
-                const double *q8 = m8, *qh = mh;
-                for (int ks = 0; ks < kt; ++ks) {
-                    const double b8v = b8n * (is_es ? f8 : lds_f64(sc8 + 32u * ks)), bhv = bhn * (is_es ? fh : lds_f64(sch + 32u * ks));
-                    if (ks + 1 < kt) { q8 += bstep; qh += bstep; b8n = __ldg(q8); bhn = __ldg(qh); }
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + 32u * ks), b8v);
-                        dmma_8x8x4(acc[c][0], acc[c][1], lds_f64(a8[c] + dproc + 32u * ks), bhv);
-                    }
-                }
-                // ---- epilogue on the accumulator registers ----------------------------------------------
-                double r[kMC][2];
-                bool vr[kMC];
-#pragma unroll
-                for (int c = 0; c < kMC; ++c) {
-                    const int row = 8 * (m0 + c) + fg;
-                    vr[c] = m0 + c < mt && row < nrow;
-                    const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
-                    r[c][0] = w * acc[c][0];
-                    r[c][1] = w * acc[c][1];
-                }
-                if (MODE == kModeLlh) {
-                    double2 o0[kMC], o1[kMC];
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        const int row = 8 * (m0 + c) + fg;
-                        o0[c] = (vr[c] && v0) ? __ldg(ol + row * nR + j0) : make_double2(0.0, 0.0);
-                        o1[c] = (vr[c] && v1) ? __ldg(ol + row * nR + j0 + 1) : make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        const double t0 = poisson_term((vr[c] && v0) ? r[c][0] : 1.0, o0[c].x, o0[c].y, fl);
-                        const double t1 = poisson_term((vr[c] && v1) ? r[c][1] : 1.0, o1[c].x, o1[c].y, fl);
-                        part += ((vr[c] && v0) ? t0 : 0.0) + ((vr[c] && v1) ? t1 : 0.0);
-                    }
-                } else if (MODE == kModeAsym) {
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        const double s01 = ((vr[c] && v0) ? r[c][0] : 0.0) + ((vr[c] && v1) ? r[c][1] : 0.0);
-                        const bool is_day = m0 + c == 0 && fg == 0;
-                        if (is_es) { if (is_day) d_es += s01; else n_es += s01; }
-                        else { if (is_day) d_cc += s01; else n_cc += s01; }
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        if (!vr[c]) continue;
-                        const int row = 8 * (m0 + c) + fg;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int jx = j0 + h;
-                            if (jx >= nR) continue;
-                            double v = r[c][h];
-                            if (MODE == kModePerbin) {
-                                v = (jx >= idx0 && jx < nR - 1) ? perbin_term(v, obs[row * nR + jx]) : 0.0;
-                                if (oob) v = -INFINITY;
-                            }
-                            if (row == 0) {
-                                if (day) day[b * nR + jx] = v;
-                            } else if (night) {
-                                night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = v;
-                            }
-                        }
-                    }
-                }
+        FoldTask<MODE> F{T, L, D, O, p8s, phs, scale, cst_es, cst_cc, f8, fh, b, ldp, nrow, mt, kt, bte, btc, oob};
+        // Column block (8 reco bins of one channel) x row tiles.  A point that runs its own oscillation stage shares
+        // the SM with another CTA that is mostly propagating, and one column block per warp with all row tiles in
+        // flight (most independent logarithm chains) is the fastest arrangement even though it leaves warps without
+        // a block idle.  When the points of a group share one oscillation stage the kernel is fold-bound: there the
+        // work is cut finer -- per column block, groups of kMCa row tiles, then the remainder in groups of kMCb --
+        // and dealt by the host's longest-first assignment (D.fold_owner) so that all kWarps warps carry the same
+        // number of tiles (6 column blocks x 7 row tiles in the default binning: six warps take 5 tiles, two take 3 x 2).
+        const int nb = bte + btc;
+        const int na = mt / kMCa, nbm = (mt - kMCa * na + kMCb - 1) / kMCb;
+        const int ntask = nb * (na + nbm);
+        if (kThr && L.group > 1 && D.fold_ntask == ntask) {
+            for (int t = 0; t < ntask; ++t) {
+                if ((int)D.fold_owner[t] != warp) continue;
+                const bool big = t < nb * na;
+                const int tt = big ? t : t - nb * na;
+                const int pass = tt / nb, col = tt - pass * nb;
+                if (col < bte ? !D.es_mode : !D.cc_mode) continue;
+                if (big) F.template run<kMCa>(col, kMCa * pass, part, fl, d_es, n_es, d_cc, n_cc);
+                else F.template run<kMCb>(col, kMCa * na + kMCb * pass, part, fl, d_es, n_es, d_cc, n_cc);
+            }
+        } else {
+            for (int col = warp; col < nb; col += kWarps) {
+                if (col < bte ? !D.es_mode : !D.cc_mode) continue;
+                for (int m0 = 0; m0 < mt; m0 += kMC) F.template run<kMC>(col, m0, part, fl, d_es, n_es, d_cc, n_cc);
             }
         }
         if (MODE == kModeAsym) {

@@ -101,7 +101,10 @@ def test_grouped_equals_ungrouped(engine, tables, draw):
         p[c * g:(c + 1) * g, 8:14] = p[c * g, 8:14]
     a = engine.eval_llh(p)
     b = engine.eval_llh(p, group=g)
-    assert np.array_equal(a, b)
+    # same probabilities, same Poisson terms; the grouped fold cuts its work into finer items, so the terms are
+    # summed in a different (still fixed) order
+    assert np.max(np.abs(a - b)) < 1e-9
+    assert np.array_equal(b, engine.eval_llh(p, group=g))      # each arrangement is deterministic
 
 
 def test_chunking_and_determinism(tables, asimov, draw):
