@@ -20,7 +20,7 @@ _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
     "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_grad", "solarosc_eval_rates",
-    "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
+    "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_derived", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
     "solarosc_batcher_create", "solarosc_batcher_create_with", "solarosc_batcher_eval", "solarosc_batcher_leave",
     "solarosc_batcher_stats", "solarosc_batcher_destroy",
@@ -72,6 +72,7 @@ def load():
     L.solarosc_eval_rates.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp, dp, dp]
     L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_asymmetry.argtypes = [H, C.c_int, dp, sz, dp, dp]
+    L.solarosc_eval_derived.argtypes = [H, C.c_int, dp, sz] + [dp] * 11
     L.solarosc_eval_oscprobs.argtypes = [H, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_p1e.argtypes = [H, dp, sz, dp]
     L.solarosc_eval_llh_device.argtypes = [H, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -757,6 +757,102 @@ int solarosc_eval_asymmetry(solarosc_handle* h, int det, const double* params, s
     });
 }
 
+// Derived-mode block reduction (derive_variables_from_chain.jl:260-444).  Per chunk: oscillation stage, rates to
+// device scratch, per-sample totals (derived_sample_kernel) and the per-bin weighted sums (derived_moment_kernel,
+// carried across chunks in the slice partials); the scalar sums are accumulated here, sample by sample, from the
+// per-sample totals.
+int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, size_t n, const double* weights,
+                          const double* lref_es, const double* lref_cc, double* es_day, double* cc_day, double* ltot,
+                          double* mom_es, double* mom_cc, double* bg_mom_es, double* bg_mom_cc, double* scalars) {
+    return guarded(h, [&]() {
+        REQUIRE(params && weights, "params and weights must not be NULL");
+        REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
+        check_data(h, det);
+        const DevTables& T = h->T;
+        const DevDetector& D = T.det[det];
+        const int nZ = T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
+        const int nel_es = (1 + nZ) * nE, nel_cc = (1 + nZ) * nC, n_elem = nel_es + nel_cc + nE + nC;
+        const int n_slices = 32;
+        const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
+        const int step = std::max(1, std::min(h->chunk, 1024));
+        const size_t fixed = (size_t)nel_es + nel_cc + (size_t)(n_slices + 1) * kDerivedQ * n_elem;
+        h->ensure_scratch((per * step + 5 * (size_t)step + fixed) * sizeof(double));
+        double* d_lref_es = h->d_scratch;
+        double* d_lref_cc = d_lref_es + nel_es;
+        double* d_partial = d_lref_cc + nel_cc;
+        double* d_out = d_partial + (size_t)n_slices * kDerivedQ * n_elem;
+        double* d_w = d_out + (size_t)kDerivedQ * n_elem;
+        double* d_ltot = d_w + step;
+        double* d_rates = d_ltot + 4 * (size_t)step;
+        if (lref_es) CK(cudaMemcpyAsync(d_lref_es, lref_es, nel_es * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (lref_cc) CK(cudaMemcpyAsync(d_lref_cc, lref_cc, nel_cc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        std::vector<double> acc(21, 0.0), lt((size_t)4 * step);
+        h->launches = 0;
+        if (n == 0) CK(cudaMemsetAsync(d_out, 0, (size_t)kDerivedQ * n_elem * sizeof(double), h->stream));
+        for (size_t b0 = 0; b0 < n; b0 += step) {
+            const int nb = (int)std::min<size_t>(step, n - b0);
+            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(d_w, weights + b0, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
+            double* sp = d_rates;
+            RatesOut O{};
+            O.es_day = sp; sp += (size_t)nb * nE;
+            O.es_night = sp; sp += (size_t)nb * nZ * nE;
+            O.cc_day = sp; sp += (size_t)nb * nC;
+            O.cc_night = sp; sp += (size_t)nb * nZ * nC;
+            O.bg_es = sp; sp += (size_t)nb * nE;
+            O.bg_cc = sp;
+            {   // rates with row-major night arrays whatever the handle's host layout is
+                RatesLaunch L = rates_launch(h, nb, 1, det);
+                L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
+                rates_kernel<kModeRates><<<nb, kThreads, rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco), h->stream>>>(T, L, h->d_params, h->d_osc, O);
+                CK(cudaGetLastError());
+                ++h->launches;
+            }
+            DerivedLaunch L{nb, n_slices, h->P, det, nZ, nE, nC, D.index_es - 1, D.index_cc - 1, b0 == 0 ? 1 : 0, T.earth_unc, T.n_layers};
+            DerivedIn I{O.es_day, O.es_night, O.cc_day, O.cc_night, O.bg_es, O.bg_cc, D.obs_es, D.obs_cc,
+                        lref_es ? d_lref_es : nullptr, lref_cc ? d_lref_cc : nullptr, h->d_params, d_w};
+            derived_sample_kernel<<<nb, 256, 0, h->stream>>>(L, I, d_ltot);
+            derived_moment_kernel<<<dim3((n_elem + 255) / 256, n_slices), 256, 0, h->stream>>>(L, I, d_partial);
+            CK(cudaGetLastError());
+            h->launches += 2;
+            CK(cudaMemcpyAsync(lt.data(), d_ltot, (size_t)4 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (es_day) CK(cudaMemcpyAsync(es_day + b0 * nE, O.es_day, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (cc_day) CK(cudaMemcpyAsync(cc_day + b0 * nC, O.cc_day, (size_t)nb * nC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < nb; ++i) {   // derive...:343-348, 388-417, in sample order
+                const double w = weights[b0 + i], t1 = params[(b0 + i) * h->P + 0], t2 = params[(b0 + i) * h->P + 2];
+                acc[0] += w; acc[1] += w * t1; acc[2] += w * (t1 * t1); acc[3] += w * t2; acc[4] += w * (t2 * t2);
+                for (int g = 0; g < 4; ++g) {
+                    const double l = lt[(size_t)4 * i + g];
+                    acc[5 + 4 * g + 0] += w * l; acc[5 + 4 * g + 1] += w * (l * l);
+                    acc[5 + 4 * g + 2] += w * (l * t1); acc[5 + 4 * g + 3] += w * (l * t2);
+                }
+            }
+            if (ltot) std::memcpy(ltot + 4 * b0, lt.data(), (size_t)4 * nb * sizeof(double));
+        }
+        if (n > 0) {
+            derived_finish_kernel<<<(kDerivedQ * n_elem + 255) / 256, 256, 0, h->stream>>>(n_slices, n_elem, d_partial, d_out);
+            CK(cudaGetLastError());
+            ++h->launches;
+        }
+        std::vector<double> out((size_t)kDerivedQ * n_elem);
+        CK(cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int q = 0; q < kDerivedQ; ++q) {
+            const double* src = out.data() + (size_t)q * n_elem;
+            if (mom_es) std::memcpy(mom_es + (size_t)q * nel_es, src, nel_es * sizeof(double));
+            if (mom_cc) std::memcpy(mom_cc + (size_t)q * nel_cc, src + nel_es, nel_cc * sizeof(double));
+            if (q < 2) {
+                if (bg_mom_es) std::memcpy(bg_mom_es + (size_t)q * nE, src + nel_es + nel_cc, nE * sizeof(double));
+                if (bg_mom_cc) std::memcpy(bg_mom_cc + (size_t)q * nC, src + nel_es + nel_cc + nE, nC * sizeof(double));
+            }
+        }
+        if (scalars) std::memcpy(scalars, acc.data(), 21 * sizeof(double));
+        return (int)SOLAROSC_OK;
+    });
+}
+
 int solarosc_eval_oscprobs(solarosc_handle* h, const double* params, size_t n, double* day_8b, double* night_8b,
                            double* day_hep, double* night_hep) {
     return guarded(h, [&]() {

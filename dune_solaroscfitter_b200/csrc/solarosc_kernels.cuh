@@ -858,6 +858,116 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
 }
 
 // ------------------------------------------------------------------------------------------
+// Derived-mode reductions over a block of chain samples (reference derive_variables_from_chain.jl:260-444): the
+// replay loop's weighted moments accumulated on the device, so that a block of samples returns O(bins) numbers
+// instead of 49 kB of rate arrays per sample.  Input: the rate arrays of the block as rates_kernel<kModeRates>
+// wrote them (row-major night arrays) in device scratch.
+//   element e of channel c: row = e / nR (0 = day, 1 + z = night zenith bin z), j = e % nR
+//   l(e)  = perbin Poisson term (likelihood_statistical.jl:31-57; bins idx..n-1, the overflow bin excluded)
+//           minus the caller's reference l_ref(e)                       (derive...:357-361)
+//   sums  = [ sum w r, sum w r^2 (bins idx..n: derive...:285-313),  sum w l, sum w l^2, sum w l th1, sum w l th2 (:420-444) ]
+//   bg    = [ sum w bg/2, sum w (bg/2)^2 ]                              (derive...:322-339)
+// HBM-bound streaming reduction: every rate is read once per kernel.
+// ------------------------------------------------------------------------------------------
+struct DerivedLaunch {
+    int n_samples, n_slices, param_stride, det;
+    int nZ, nE, nC, idx_es, idx_cc;      // idx_*: 0-based first bin of the likelihood
+    int first;                           // 1: partial sums start from zero, 0: they continue an earlier block
+    int earth_unc, n_layers;
+};
+struct DerivedIn {
+    const double *es_day, *es_night, *cc_day, *cc_night, *bg_es, *bg_cc;   // [n][..] device scratch
+    const double *obs_es, *obs_cc;       // [1+nZ][nR]
+    const double *lref_es, *lref_cc;     // [1+nZ][nR] or nullptr
+    const double *params, *weights;
+};
+constexpr int kDerivedQ = 6;
+
+__device__ __forceinline__ bool derived_oob(const DerivedLaunch& L, const double* p) {
+    bool oob = false;
+    if (L.earth_unc)
+        for (int k = 0; k < L.n_layers; ++k) {
+            const double x = p[SOLAROSC_N_FIXED_PARAMS + k];
+            oob |= !(x >= 0.0 && x <= 2.0);
+        }
+    return oob;
+}
+// rate and centred per-bin term of element e of a channel for sample b
+__device__ __forceinline__ void derived_element(int e, int nR, int nZ, int idx0, size_t b, const double* day, const double* night,
+                                                const double* obs, const double* lref, bool oob, double& r, double& l, bool& above) {
+    const int row = e / nR, j = e - row * nR;
+    r = row == 0 ? day[b * nR + j] : night[(b * nZ + (row - 1)) * nR + j];
+    above = j >= idx0;
+    double v = (j >= idx0 && j < nR - 1) ? perbin_term(r, obs[e]) : 0.0;
+    if (oob) v = -INFINITY;              // make_perbin_likelihood, likelihood_builder.jl:271-282
+    l = v - (lref ? lref[e] : 0.0);
+}
+
+// One CTA per sample: totals of the centred per-bin terms per (channel, day/night): out[b][4] = ES night, ES day,
+// CC night, CC day (derive...:388-417).
+__global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch L, const DerivedIn I, double* __restrict__ ltot) {
+    __shared__ double red[8];
+    const size_t b = blockIdx.x;
+    const bool oob = derived_oob(L, I.params + b * L.param_stride);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int nel_es = (1 + L.nZ) * L.nE, nel_cc = (1 + L.nZ) * L.nC;
+    for (int t = threadIdx.x; t < nel_es + nel_cc; t += blockDim.x) {
+        const bool es = t < nel_es;
+        const int e = es ? t : t - nel_es, nR = es ? L.nE : L.nC;
+        double r, l;
+        bool above;
+        derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
+                        es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, oob, r, l, above);
+        acc[(es ? 0 : 2) + (e < nR ? 1 : 0)] += l;
+    }
+    for (int k = 0; k < 4; ++k) {
+        const double s = block_sum(acc[k], red);
+        if (threadIdx.x == 0) ltot[b * 4 + k] = s;
+    }
+}
+
+// grid (elements / 256, n_slices): thread = one element, slice s walks samples s, s + n_slices, ... in order and adds
+// into partial[s][kDerivedQ][n_elem]; derived_finish_kernel adds the slices in order.  Deterministic.
+__global__ void __launch_bounds__(256) derived_moment_kernel(const DerivedLaunch L, const DerivedIn I, double* __restrict__ partial) {
+    const int nel_es = (1 + L.nZ) * L.nE, nel_cc = (1 + L.nZ) * L.nC, n_elem = nel_es + nel_cc + L.nE + L.nC;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_elem) return;
+    double q[kDerivedQ];
+    double* out = partial + (size_t)blockIdx.y * kDerivedQ * n_elem + t;
+#pragma unroll
+    for (int k = 0; k < kDerivedQ; ++k) q[k] = L.first ? 0.0 : out[(size_t)k * n_elem];
+    for (size_t b = blockIdx.y; b < (size_t)L.n_samples; b += L.n_slices) {
+        const double w = I.weights[b];
+        const double* p = I.params + b * L.param_stride;
+        if (t < nel_es + nel_cc) {
+            const bool es = t < nel_es;
+            const int e = es ? t : t - nel_es, nR = es ? L.nE : L.nC;
+            double r, l;
+            bool above;
+            derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
+                            es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, derived_oob(L, p), r, l, above);
+            if (above) { q[0] += w * r; q[1] += w * (r * r); }
+            q[2] += w * l; q[3] += w * (l * l); q[4] += w * (l * p[0]); q[5] += w * (l * p[2]);
+        } else {
+            const int e = t - nel_es - nel_cc;
+            const double h = 0.5 * (e < L.nE ? I.bg_es[b * L.nE + e] : I.bg_cc[b * L.nC + (e - L.nE)]);
+            q[0] += w * h; q[1] += w * (h * h);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kDerivedQ; ++k) out[(size_t)k * n_elem] = q[k];
+}
+
+__global__ void __launch_bounds__(256) derived_finish_kernel(int n_slices, int n_elem, const double* __restrict__ partial,
+                                                             double* __restrict__ out /* [kDerivedQ][n_elem] */) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= kDerivedQ * n_elem) return;
+    double s = 0.0;
+    for (int k = 0; k < n_slices; ++k) s += partial[(size_t)k * kDerivedQ * n_elem + t];
+    out[t] = s;
+}
+
+// ------------------------------------------------------------------------------------------
 // Stand-alone Poisson reduction: one CTA per (expected, measured) vector pair
 // (reference poissonLogLikelihood, likelihood_statistical.jl:1-28; the shape timed by
 //  tests/benchmark_likelihoods.jl:10-19)

@@ -2,8 +2,9 @@
 
 The reference's `RunMode: derived` replays a stored chain one sample at a time
 (`derive_variables_from_chain.jl:214-447`); with the engine the rates of a whole block of samples come
-back from one `expected_rates_batch` call and the reductions below run over the batch axis.  Moving these
-reductions onto the device is the next step; the formulas are the reference's.
+back from one `expected_rates_batch` call and the reductions below run over the batch axis.  The engine does
+the same reductions on the device (`SolarOscEngine.eval_derived` -> `solarosc_eval_derived`); the numpy versions
+here are the host-side statement of the formulas and what the tests compare the device sums with.
 """
 from __future__ import annotations
 
@@ -37,3 +38,38 @@ def weighted_moments(rates: np.ndarray, weights: np.ndarray, index: int) -> Tupl
     m1[..., k:] = (w * rates[..., k:]).sum(axis=0)
     m2[..., k:] = (w * rates[..., k:] ** 2).sum(axis=0)
     return m1, m2
+
+
+def replay_block_sums(rates: dict, perbin: dict, lref: dict, params: np.ndarray, weights: np.ndarray,
+                      index_es: int, index_cc: int) -> dict:
+    """The replay loop of derive_variables_from_chain.jl:260-444 over a block of samples, written as that loop.
+
+    `rates` / `perbin` hold the per-sample arrays (ES_day [B, n], ES_night [B, n_cosz, n], ... and BG_*_tot for the
+    rates), `lref` the per-bin terms the loop centres on.  Returns the same keys as SolarOscEngine.eval_derived."""
+    B = len(weights)
+    nz = rates["ES_night"].shape[1]
+    out = {"scalars": np.zeros(21), "ltot": np.zeros((B, 4))}
+    for ch, idx in (("ES", index_es), ("CC", index_cc)):
+        n = rates[ch + "_day"].shape[1]
+        out["mom_" + ch] = np.zeros((6, 1 + nz, n))
+        out["bg_mom_" + ch] = np.zeros((2, n))
+    for i in range(B):
+        w, t1, t2 = float(weights[i]), float(params[i, 0]), float(params[i, 2])
+        sc = out["scalars"]
+        sc[0] += w; sc[1] += w * t1; sc[2] += w * t1 ** 2; sc[3] += w * t2; sc[4] += w * t2 ** 2
+        for c, (ch, idx) in enumerate((("ES", index_es), ("CC", index_cc))):
+            k = idx - 1
+            r = np.vstack([rates[ch + "_day"][i][None, :], rates[ch + "_night"][i]])
+            l = np.vstack([perbin[ch + "_day"][i][None, :], perbin[ch + "_night"][i]]) - \
+                np.vstack([np.asarray(lref[ch + "_day"])[None, :], np.asarray(lref[ch + "_night"])])
+            m = out["mom_" + ch]
+            m[0][:, k:] += w * r[:, k:]
+            m[1][:, k:] += w * r[:, k:] ** 2
+            m[2] += w * l; m[3] += w * l ** 2; m[4] += w * l * t1; m[5] += w * l * t2
+            bg = 0.5 * rates["BG_" + ch + "_tot"][i]
+            out["bg_mom_" + ch][0] += w * bg
+            out["bg_mom_" + ch][1] += w * bg ** 2
+            for g, tot in ((2 * c, l[1:].sum()), (2 * c + 1, l[0].sum())):     # night, day
+                out["ltot"][i, g] = tot
+                sc[5 + 4 * g: 9 + 4 * g] += np.array([w * tot, w * tot ** 2, w * tot * t1, w * tot * t2])
+    return out

@@ -139,6 +139,36 @@ class SolarOscEngine:
         self._check(self._L.solarosc_eval_asymmetry(self._h, det, _dp(p), len(p), _dp(a_es), _dp(a_cc)))
         return a_es, a_cc
 
+    def eval_derived(self, params, weights, lref: Optional[Mapping] = None, det: int = 0) -> Dict[str, np.ndarray]:
+        """Derived-mode block sums of derive_variables_from_chain.jl:260-444 for the (thinned-in) chain samples
+        `params` with chain weights `weights`, reduced on the device.  `lref` holds the reference per-bin terms
+        (keys ES_day, ES_night, CC_day, CC_night, e.g. eval_perbin at the truth).  Returns per-sample day rates and
+        per-bin-term totals, and the weighted sums, all row-major ([.., 1 + n_cosz, n_ereco], row 0 = day)."""
+        p = self._params(params)
+        n = len(p)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if w.shape != (n,):
+            raise ValueError("weights must have one entry per sample")
+        nes, ncc = self.packed.n_ereco[det]
+        nz = self.n_cosz
+
+        def ref(ch, nr):
+            if lref is None:
+                return None
+            night = np.asarray(lref[ch + "_night"], dtype=np.float64)
+            if self.col_major:
+                night = night.T
+            return np.ascontiguousarray(np.vstack([np.asarray(lref[ch + "_day"], dtype=np.float64).reshape(1, nr), night.reshape(nz, nr)]))
+
+        r_es, r_cc = ref("ES", nes), ref("CC", ncc)
+        out = dict(ES_day=np.empty((n, nes)), CC_day=np.empty((n, ncc)), ltot=np.empty((n, 4)),
+                   mom_ES=np.empty((6, 1 + nz, nes)), mom_CC=np.empty((6, 1 + nz, ncc)),
+                   bg_mom_ES=np.empty((2, nes)), bg_mom_CC=np.empty((2, ncc)), scalars=np.empty(21))
+        self._check(self._L.solarosc_eval_derived(self._h, det, _dp(p), n, _dp(w), _dp(r_es), _dp(r_cc), _dp(out["ES_day"]),
+                                                  _dp(out["CC_day"]), _dp(out["ltot"]), _dp(out["mom_ES"]), _dp(out["mom_CC"]),
+                                                  _dp(out["bg_mom_ES"]), _dp(out["bg_mom_CC"]), _dp(out["scalars"])))
+        return out
+
     def eval_oscprobs(self, params) -> Dict[str, np.ndarray]:
         p = self._params(params)
         n, nT = len(p), self.n_etrue

@@ -30,6 +30,8 @@
  *                          propagation_main.jl:56-157 (exclusive, non-angular branch)
  *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
  *   solarosc_eval_asymmetry the per-sample D/N asymmetry of derive_variables_from_chain.jl:236-258
+ *   solarosc_eval_derived  the replay loop of derive_variables_from_chain.jl:260-444 over a block of chain samples
+ *                          (weighted rate moments, centred per-bin lnL moments and their totals)
  *   solarosc_eval_oscprobs compute_shared_osc_probs, propagation_main.jl:47-54
  *   solarosc_eval_p1e      Osc.NumOsc.Fast.osc_prob_earth, osc.jl:448-477
  *   solarosc_poisson_llh   poissonLogLikelihood, likelihood_statistical.jl:1-28
@@ -186,6 +188,24 @@ int solarosc_eval_perbin(solarosc_handle *h, int det, const double *params, size
  * point come back instead of the 49 kB of rate arrays.  Either output may be NULL. */
 int solarosc_eval_asymmetry(solarosc_handle *h, int det, const double *params, size_t n_points, double *asym_es,
                             double *asym_cc);
+
+/* Derived-mode reductions over a block of (thinned-in) chain samples of detector det, accumulated on the device
+ * (derive_variables_from_chain.jl:260-444): O(bins) numbers come back instead of 49 kB of rate arrays per sample.
+ * The caller adds the block sums of successive calls.  Array outputs are row-major whatever col_major says; any
+ * output may be NULL.
+ *   weights   [n]  chain weights w
+ *   lref_es / lref_cc  [1 + n_cosz][n_ereco] reference per-bin terms (row 0 = day) the per-bin terms are centred on
+ *             (the reference uses the per-bin terms at the Asimov truth, derive...:190-207); NULL = zeros
+ *   es_day / cc_day    [n][n_ereco] day rates per sample (the posterior-predictive sample lists, derive...:315-332)
+ *   ltot      [n][4]  totals of the centred per-bin terms: ES night, ES day, CC night, CC day
+ *   mom_es / mom_cc    [6][1 + n_cosz][n_ereco]: sum w r, sum w r^2 (bins from the threshold on, zero below),
+ *             sum w l, sum w l^2, sum w l sin2_th12, sum w l dm2_21 with l the centred per-bin term
+ *   bg_mom_es / bg_mom_cc  [2][n_ereco]: sum w (BG/2), sum w (BG/2)^2
+ *   scalars   [21]: sum w, sum w th1, sum w th1^2, sum w th2, sum w th2^2 (th1 = sin2_th12, th2 = dm2_21), then for
+ *             each group of ltot: sum w L, sum w L^2, sum w L th1, sum w L th2 */
+int solarosc_eval_derived(solarosc_handle *h, int det, const double *params, size_t n_points, const double *weights,
+                          const double *lref_es, const double *lref_cc, double *es_day, double *cc_day, double *ltot,
+                          double *mom_es, double *mom_cc, double *bg_mom_es, double *bg_mom_cc, double *scalars);
 
 /* nu_e survival probabilities at analysis resolution: day [n][n_etrue], night [n][n_cosz][n_etrue]
  * (col_major: [n][n_etrue][n_cosz]); nu_other = 1 - nu_e. */

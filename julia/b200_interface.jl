@@ -277,4 +277,31 @@ function compute_shared_osc_probs(params, solarModel; nz::Int, nT::Int)
             nuother_8B_day=1 .- d8, nuother_8B_night=1 .- n8, nuother_hep_day=1 .- dh, nuother_hep_night=1 .- nh)
 end
 
+"""
+    derived_block_sums(params, weights, lref; det, nz, nes, ncc)
+
+The replay loop of derive_variables_from_chain.jl:260-444 over a block of thinned-in chain samples, reduced on the
+device: weighted rate moments (`ESday_mean`, `ESnight_m2`, ...), the centred per-bin terms' sums (`S1_*`, `S2_*`,
+`Ssin2_*`, `Sdm2_*`), their per-sample totals and the scalar sums.  `lref` is the NamedTuple of per-bin terms at
+the Asimov truth (`ℓref_*`, derive...:190-207).  The library's arrays are row-major `[q][1 + nz][n]`; read as
+Julia arrays they are `(n, 1 + nz, q)`, so `permutedims(m[:, 2:end, q])` is the reference's `(n_cosz, n_Ereco)`
+night matrix and `m[:, 1, q]` its day vector.  The caller adds the sums of successive blocks.
+"""
+function derived_block_sums(params, weights::Vector{Float64}, lref; det::Int=0, nz::Int, nes::Int, ncc::Int)
+    M = pack_many(params); B = size(M, 2)
+    # reference terms as [1 + nz][n] row-major = (n, 1 + nz) in Julia
+    ref_es = hcat(lref.ES_day, permutedims(lref.ES_night)); ref_cc = hcat(lref.CC_day, permutedims(lref.CC_night))
+    ES_day = Array{Float64}(undef, nes, B); CC_day = Array{Float64}(undef, ncc, B); ltot = Array{Float64}(undef, 4, B)
+    mom_es = Array{Float64}(undef, nes, 1 + nz, 6); mom_cc = Array{Float64}(undef, ncc, 1 + nz, 6)
+    bg_es = Array{Float64}(undef, nes, 2); bg_cc = Array{Float64}(undef, ncc, 2); sc = Vector{Float64}(undef, 21)
+    GC.@preserve M weights ref_es ref_cc ES_day CC_day ltot mom_es mom_cc bg_es bg_cc sc begin
+        check(@ccall libb200.solarosc_eval_derived(handle[]::Handle, Cint(det)::Cint, pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t,
+            pointer(weights)::Ptr{Cdouble}, pointer(ref_es)::Ptr{Cdouble}, pointer(ref_cc)::Ptr{Cdouble},
+            pointer(ES_day)::Ptr{Cdouble}, pointer(CC_day)::Ptr{Cdouble}, pointer(ltot)::Ptr{Cdouble},
+            pointer(mom_es)::Ptr{Cdouble}, pointer(mom_cc)::Ptr{Cdouble}, pointer(bg_es)::Ptr{Cdouble},
+            pointer(bg_cc)::Ptr{Cdouble}, pointer(sc)::Ptr{Cdouble})::Cint)
+    end
+    return (ES_day=ES_day, CC_day=CC_day, ltot=ltot, mom_ES=mom_es, mom_CC=mom_cc, bg_mom_ES=bg_es, bg_mom_CC=bg_cc, scalars=sc)
+end
+
 end # module B200Osc

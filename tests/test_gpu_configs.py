@@ -141,3 +141,44 @@ def test_c5_day_night_asymmetry_and_moments(engine, tables, asimov, draw):
     assert np.max(np.abs(b_es - day_night_asymmetry(rb["ES_day"], rb["ES_night"], rb["BG_ES_tot"], int(tables["index_es"])))) < 1e-10  # background-dominated: rounding order shows
     pb = engine.eval_perbin(p[:4])
     assert pb["CC_night"].shape == (4, 50, 30) and np.all(pb["CC_night"][:, :, -1] == 0)
+
+
+def test_c5_device_block_sums_match_the_replay_loop(engine, tables, asimov, draw):
+    """solarosc_eval_derived against the replay loop (derive_variables_from_chain.jl:260-444) run in numpy on the
+    oracle's rates and per-bin terms; 1100 samples span two internal chunks."""
+    from dune_solaroscfitter_b200.derived import replay_block_sums
+    from oracle import oracle_c, oracle_np
+    n = 1100
+    p = draw(tables, n, seed=79)
+    w = np.random.default_rng(2).integers(1, 6, n).astype(float)
+    truth = np.asarray(tables["truth"], dtype=float)[None, :]
+    lref = {k: v[0] for k, v in engine.eval_perbin(truth).items()}
+    got = engine.eval_derived(p, w, lref)
+    orc = oracle_c.COracle(tables, asimov)
+    rates = orc.eval_rates(p)
+    data = asimov
+    perbin = {k: np.empty_like(rates[k]) for k in ("ES_day", "ES_night", "CC_day", "CC_night")}
+    for ch, idx in (("ES", int(tables["index_es"])), ("CC", int(tables["index_cc"]))):
+        obs = np.vstack([np.asarray(data[ch + "_day"])[None, :], np.asarray(data[ch + "_night"])])
+        for i in range(n):
+            r = np.vstack([rates[ch + "_day"][i][None, :], rates[ch + "_night"][i]])
+            t = np.zeros_like(r)
+            t[:, idx - 1:-1] = np.stack([oracle_np.perbin_poisson_log_likelihood(r[z, idx - 1:-1], obs[z, idx - 1:-1]) for z in range(len(r))])
+            perbin[ch + "_day"][i], perbin[ch + "_night"][i] = t[0], t[1:]
+    ref = replay_block_sums(rates, perbin, lref, p, w, int(tables["index_es"]), int(tables["index_cc"]))
+
+    def close(a, b, rel):
+        scale = np.maximum(np.abs(b), 1e-12 * np.max(np.abs(b)) + 1e-300)
+        return np.max(np.abs(a - b) / scale) < rel
+
+    for ch in ("ES", "CC"):
+        assert np.max(np.abs(got[ch + "_day"] - rates[ch + "_day"]) / np.maximum(np.abs(rates[ch + "_day"]), 1e-300)) < 1e-9
+        for q in range(6):
+            assert close(got["mom_" + ch][q], ref["mom_" + ch][q], 1e-8 if q >= 2 else 1e-9), (ch, q)
+        assert np.all(got["mom_" + ch][:2, :, :int(tables["index_" + ch.lower()]) - 1] == 0)      # below threshold
+        assert close(got["bg_mom_" + ch], ref["bg_mom_" + ch], 1e-12)
+    assert np.max(np.abs(got["ltot"] - ref["ltot"])) < 1e-6
+    assert close(got["scalars"], ref["scalars"], 1e-9)
+    # block sums add: two calls on the halves equal one call on the whole
+    a, b = engine.eval_derived(p[:500], w[:500], lref), engine.eval_derived(p[500:], w[500:], lref)
+    assert close(a["mom_CC"] + b["mom_CC"], got["mom_CC"], 1e-12) and close(a["scalars"] + b["scalars"], got["scalars"], 1e-12)
