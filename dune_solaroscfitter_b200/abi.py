@@ -9,7 +9,7 @@ from typing import Any, Dict, List, Mapping, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 8
 MAX_BG = 8
 N_FIXED_PARAMS = 8
@@ -22,6 +22,16 @@ PARAM_NAMES_FIXED = ("sin2_th12", "sin2_th13", "dm2_21", "integrated_8B_flux", "
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
+
+
+class DetectorExt(C.Structure):
+    """solarosc_detector_ext: tables of the inclusive / semi-inclusive / angular branches."""
+    _fields_ = [
+        ("inclusive", C.c_int32), ("angular", C.c_int32), ("n_cos", C.c_int32), ("reserved", C.c_int32),
+        ("cc_f_above", C.c_double), ("cc_f_below", C.c_double),
+        ("resp_cc_incl", _dp), ("eff_cc_incl", _dp), ("resp_cc_misid_nue", _dp), ("resp_cc_misid_nuother", _dp),
+        ("resp_es_angular", _dp), ("resp_bg_angular", _dp), ("angular_mask", _dp),
+    ]
 
 
 class Detector(C.Structure):
@@ -38,6 +48,7 @@ class Detector(C.Structure):
         ("raw_bg_es", _dp), ("raw_bg_cc", _dp),
         ("bg_es_sides", _ip), ("bg_es_par", _ip), ("bg_cc_par", _ip),
         ("obs_es_day", _dp), ("obs_es_night", _dp), ("obs_cc_day", _dp), ("obs_cc_night", _dp),
+        ("ext", C.POINTER(DetectorExt)),
     ]
 
 
@@ -63,6 +74,8 @@ _DET_F64 = ("unosc_es_nue_8b", "unosc_es_nuother_8b", "unosc_cc_8b", "unosc_es_n
             "unosc_es_nuother_hep", "unosc_cc_hep", "log_e_norm", "resp_es_nue", "resp_es_nuother",
             "resp_cc", "eff_es_nue", "eff_es_nuother", "eff_cc", "raw_bg_es", "raw_bg_cc")
 _DET_I32 = ("bg_es_sides", "bg_es_par", "bg_cc_par")
+_EXT_F64 = ("resp_cc_incl", "eff_cc_incl", "resp_cc_misid_nue", "resp_cc_misid_nuother", "resp_es_angular",
+            "resp_bg_angular", "angular_mask")
 _OBS = (("obs_es_day", "ES_day"), ("obs_es_night", "ES_night"), ("obs_cc_day", "CC_day"), ("obs_cc_night", "CC_night"))
 
 
@@ -98,7 +111,9 @@ class PackedTables:
         k = self._keep
         n_det = len(detectors)
         self.det_array = (Detector * n_det)()
+        self.ext_array = (DetectorExt * n_det)()
         self.n_norms = []
+        self.n_cos = []
         for d, src in enumerate(detectors):
             ds = self.det_array[d]
             ds.es_mode = int(src.get("es_mode", es_mode)) if hasattr(src, "get") else int(es_mode)
@@ -119,6 +134,19 @@ class PackedTables:
                 else:
                     a = _f64(obs[key]); k.append(a); setattr(ds, cname, _ptr(a, _dp))
             self.n_norms.append((int(np.count_nonzero(src["bg_es_par"])), int(np.count_nonzero(src["bg_cc_par"]))))
+            # optional keys `inclusive` (0 / 1 / 2 semi-inclusive) and `angular` select the other analysis branches
+            incl = int(src["inclusive"]) if "inclusive" in src else 0
+            ang = int(src["angular"]) if "angular" in src else 0
+            self.n_cos.append(int(src["n_cos"]) if ang else 1)
+            if incl or ang:
+                x = self.ext_array[d]
+                x.inclusive, x.angular, x.n_cos = incl, ang, int(src["n_cos"]) if ang else 0
+                x.cc_f_above = float(src["cc_f_above"]) if incl == 2 else 1.0
+                x.cc_f_below = float(src["cc_f_below"]) if incl == 2 else 1.0
+                for name in _EXT_F64:
+                    if name in src and src[name] is not None:
+                        a = _f64(src[name]); k.append(a); setattr(x, name, _ptr(a, _dp))
+                ds.ext = C.pointer(x)
         t = self.struct = Tables()
         t.n_etrue = int(len(shared["e_calc"]) // 2)
         t.n_cosz = int(len(shared["exposure_weights"]))

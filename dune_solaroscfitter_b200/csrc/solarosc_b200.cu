@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "solarosc_grad.cuh"
+#include "solarosc_general.cuh"
 
 using namespace solarosc;
 
@@ -52,6 +53,8 @@ struct solarosc_handle {
     int device = 0, sm_count = 148, chunk = 4096, P = 0;
     int max_ereco = 0;
     int n_es[kMaxDet]{}, n_cc[kMaxDet]{};
+    int n_cos[kMaxDet]{};        // cos-scatter bins of the ES arrays (1 unless the detector uses the angular reconstruction)
+    bool gen = false;            // some detector runs an inclusive / semi-inclusive / angular branch: gen_kernel serves every call
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D / D2H of the host-buffer pipeline
     cudaEvent_t ev_in[2]{}, ev_done[2]{}, ev_out[2]{};
@@ -63,6 +66,7 @@ struct solarosc_handle {
     // per-detector data buffers (device, [1+n_cosz][n_ereco]) kept so set_data can overwrite them
     double *d_obs_es[kMaxDet]{}, *d_obs_cc[kMaxDet]{}, *d_log_es[kMaxDet]{}, *d_log_cc[kMaxDet]{};
     double2 *d_ol_es[kMaxDet]{}, *d_ol_cc[kMaxDet]{};   // (m, log m) interleaved: one 16-byte load per Poisson term
+    double2* d_ol_ang[kMaxDet]{};                        // angular ES data, [1 + n_cosz][n_ereco_es][n_cos]
     bool has_data[kMaxDet]{};
     // workspaces
     double* d_params2[2]{};      // double-buffered parameter chunks
@@ -150,7 +154,24 @@ void upload_data(solarosc_handle* h, int d, const double* es_day, const double* 
         CK(cudaMemcpy(d_log, lg.data(), lg.size() * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_ol, ol.data(), ol.size() * sizeof(double), cudaMemcpyHostToDevice));
     };
-    pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d], h->d_ol_es[d]);
+    if (h->T.det[d].ang) {
+        // reference shapes (n_cos, n_E) and (n_cos, n_E, n_cosz): [c][j], [c][j][z] row-major, [j][c], [z][j][c] as Julia
+        // lays them out; device layout [row][j][c]
+        const int nC = h->T.det[d].n_cos, nR = h->n_es[d];
+        std::vector<double> ol((size_t)2 * (1 + nZ) * nR * nC);
+        for (int row = 0; row <= nZ; ++row)
+            for (int j = 0; j < nR; ++j)
+                for (int c = 0; c < nC; ++c) {
+                    double m;
+                    if (row == 0) m = cm ? es_day[(size_t)j * nC + c] : es_day[(size_t)c * nR + j];
+                    else m = cm ? es_night[((size_t)(row - 1) * nR + j) * nC + c] : es_night[((size_t)c * nR + j) * nZ + (row - 1)];
+                    const size_t o = ((size_t)row * nR + j) * nC + c;
+                    ol[2 * o] = m; ol[2 * o + 1] = m > 0.0 ? std::log(m) : 0.0;
+                }
+        CK(cudaMemcpy(h->d_ol_ang[d], ol.data(), ol.size() * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d], h->d_ol_es[d]);
+    }
     pack(cc_day, cc_night, h->n_cc[d], h->d_obs_cc[d], h->d_log_cc[d], h->d_ol_cc[d]);
     h->has_data[d] = true;
 }
@@ -276,6 +297,64 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
                     bh[(size_t)i * lc + j] = s.unosc_cc_hep[i] * xc;
                 }
             }
+            D.cc_out = D.cc_mode; D.f_below = 1.0;
+            if (const solarosc_detector_ext* x = s.ext; x && (x->inclusive != 0 || x->angular != 0)) {
+                // inclusive / semi-inclusive / angular branches: extra constant matrices (solarosc_general.cuh)
+                h->gen = true;
+                REQUIRE(x->inclusive >= 0 && x->inclusive <= 2, "ext.inclusive must be 0, 1 or 2");
+                D.incl = x->inclusive; D.ang = x->angular != 0;
+                if (D.incl) {
+                    REQUIRE(x->resp_cc_incl && x->eff_cc_incl, "inclusive analysis needs resp_cc_incl and eff_cc_incl");
+                    REQUIRE(D.es_mode || !D.cc_mode, "inclusive analysis with ES_mode off and CC_mode on is not supported");
+                    const double f_above = D.incl == 2 ? x->cc_f_above : 1.0;
+                    if (D.cc_mode) {   // compute_CC_inclusive_event_rates, propagation_reco.jl:139-170
+                        const std::vector<double> ri = to_row_major(x->resp_cc_incl, nT, D.n_es, cm);
+                        std::vector<double> x8((size_t)kp * le, 0.0), xh(x8);
+                        for (int i = 0; i < nT; ++i)
+                            for (int j = 0; j < D.n_es; ++j) {
+                                const double xc = f_above * (0.5 * x->eff_cc_incl[j] * ri[(size_t)i * D.n_es + j]);
+                                x8[(size_t)i * le + j] = s.unosc_cc_8b[i] * xc;
+                                xh[(size_t)i * le + j] = s.unosc_cc_hep[i] * xc;
+                            }
+                        D.xs8 = h->upload_vec(x8); D.xsh = h->upload_vec(xh);
+                    }
+                    if (D.incl == 1) D.cc_out = 0;   // CC arrays are zero and use_CC is false (propagation_main.jl:148-150, likelihood_main.jl:12)
+                    if (D.incl == 2) {
+                        D.f_below = x->cc_f_below;
+                        for (auto& v : b8) v *= D.f_below;
+                        for (auto& v : bh) v *= D.f_below;
+                        if (D.es_mode) {   // compute_ES_misID_CC_event_rates, propagation_reco.jl:187-199
+                            REQUIRE(x->resp_cc_misid_nue && x->resp_cc_misid_nuother, "semi-inclusive analysis needs the mis-ID responses");
+                            const std::vector<double> mn = to_row_major(x->resp_cc_misid_nue, nT, D.n_cc, cm);
+                            const std::vector<double> mo = to_row_major(x->resp_cc_misid_nuother, nT, D.n_cc, cm);
+                            std::vector<double> y8((size_t)kp * lc, 0.0), yh(y8), yc8(lc, 0.0), ych(lc, 0.0);
+                            for (int i = 0; i < nT; ++i)
+                                for (int j = 0; j < D.n_cc; ++j) {
+                                    const double xe = s.eff_cc[j] * mn[(size_t)i * D.n_cc + j], xo = s.eff_cc[j] * mo[(size_t)i * D.n_cc + j];
+                                    y8[(size_t)i * lc + j] = 0.5 * (s.unosc_es_nue_8b[i] * xe - s.unosc_es_nuother_8b[i] * xo);
+                                    yh[(size_t)i * lc + j] = 0.5 * (s.unosc_es_nue_hep[i] * xe - s.unosc_es_nuother_hep[i] * xo);
+                                    yc8[j] += 0.5 * s.unosc_es_nuother_8b[i] * xo;
+                                    ych[j] += 0.5 * s.unosc_es_nuother_hep[i] * xo;
+                                }
+                            D.yp8 = h->upload_vec(y8); D.yph = h->upload_vec(yh); D.yc8 = h->upload_vec(yc8); D.ych = h->upload_vec(ych);
+                        }
+                    }
+                }
+                if (D.ang) {   // compute_ES_angular_event_rates, propagation_reco.jl:66-108
+                    REQUIRE(x->n_cos > 0 && x->resp_es_angular && x->resp_bg_angular && x->angular_mask, "angular analysis needs n_cos and the angular tables");
+                    D.n_cos = x->n_cos;
+                    const std::vector<double> ra = to_row_major(x->resp_es_angular, D.n_cos, D.n_es, cm);
+                    const std::vector<double> rb = to_row_major(x->resp_bg_angular, D.n_cos, D.n_es, cm);
+                    std::vector<double> am((size_t)D.n_es * D.n_cos), bm(am.size());
+                    for (int cs = 0; cs < D.n_cos; ++cs)
+                        for (int j = 0; j < D.n_es; ++j) {
+                            am[(size_t)j * D.n_cos + cs] = x->angular_mask[cs] * ra[(size_t)cs * D.n_es + j];
+                            bm[(size_t)j * D.n_cos + cs] = rb[(size_t)cs * D.n_es + j];
+                        }
+                    D.angm = h->upload_vec(am); D.bgang = h->upload_vec(bm);
+                }
+            }
+            h->n_cos[d] = D.ang ? D.n_cos : 1;
             D.a8 = h->upload_vec(a8); D.ah = h->upload_vec(ah); D.c8 = h->upload_vec(c8); D.ch = h->upload_vec(chh);
             D.b8 = h->upload_vec(b8); D.bh = h->upload_vec(bh);
             // copies that start at the threshold bin (likelihood / asymmetry modes)
@@ -336,6 +415,11 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaMemset(h->d_ol_es[d], 0, ne * sizeof(double2))); CK(cudaMemset(h->d_ol_cc[d], 0, nc * sizeof(double2)));
         D.obs_es = h->d_obs_es[d]; D.logobs_es = h->d_log_es[d]; D.obs_cc = h->d_obs_cc[d]; D.logobs_cc = h->d_log_cc[d];
         D.ol_es = h->d_ol_es[d]; D.ol_cc = h->d_ol_cc[d];
+        if (D.ang) {
+            h->d_ol_ang[d] = h->dalloc<double2>(ne * D.n_cos);
+            CK(cudaMemset(h->d_ol_ang[d], 0, ne * D.n_cos * sizeof(double2)));
+            D.ol_es_ang = h->d_ol_ang[d];
+        }
         if (s.obs_es_day && s.obs_es_night && s.obs_cc_day && s.obs_cc_night)
             upload_data(h, d, s.obs_es_day, s.obs_es_night, s.obs_cc_day, s.obs_cc_night);
     }
@@ -361,6 +445,8 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(rates_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(rates_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(rates_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(gen_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(gen_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
@@ -437,6 +523,19 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     const DevTables& T = h->T;
     const RatesLaunch L = rates_launch(h, n, group, det_only);
     const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    if (h->gen) {
+        if (mode != kModeLlh && mode != kModeRates)
+            throw ArgFail{"per-bin, asymmetry and derived calls serve the exclusive, non-angular analysis only"};
+        const int d = det_only >= 0 ? det_only : 0;
+        const bool cm = h->cfg.col_major != 0;
+        const long long nC = h->n_cos[d], nE = h->n_es[d], nZ = T.n_cosz;
+        const GenLaunch GL = cm ? GenLaunch{1, nC, 1, nC, nC * nE} : GenLaunch{nE, 1, nE * nZ, nZ, 1};
+        if (mode == kModeLlh) gen_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        else gen_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        CK(cudaGetLastError());
+        ++h->launches;
+        return;
+    }
     if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     else if (mode == kModeAsym) rates_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
     else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
@@ -450,7 +549,7 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
 bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid,
                 int mode = kModeLlh, int det_only = -1) {
     const int n_osc = n / group;
-    if (h->fused_ok && h->use_fused && n_osc >= h->sm_count) {
+    if (h->fused_ok && h->use_fused && !h->gen && n_osc >= h->sm_count) {
         const RatesLaunch L = rates_launch(h, n, group, det_only);
         const int grid = std::min(n_osc, h->fused_grid);
         if (mode == kModeLlh) llh_kernel<kModeLlh><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
@@ -555,8 +654,9 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     if (mode == kModePerbin) check_data(h, det);
     REQUIRE(h->rates_ok, "binning too large for the fold's shared-memory tile");
     const int nZ = h->T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
-    const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
-    const int step = std::max(1, std::min(h->chunk, 1024));
+    const size_t nA = (size_t)h->n_cos[det] * nE;   // ES array entries per row (cos-scatter axis in the angular analysis)
+    const size_t per = (size_t)(1 + nZ) * (nA + nC) + nE + nC;
+    const int step = std::max(1, std::min(h->chunk, nA > (size_t)nE ? 128 : 1024));
     h->ensure_scratch(per * step * sizeof(double));
     h->launches = 0;
     for (size_t b0 = 0; b0 < n; b0 += step) {
@@ -565,8 +665,8 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
         launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
         double* s = h->d_scratch;
         RatesOut O{};
-        O.es_day = s; s += (size_t)nb * nE;
-        O.es_night = s; s += (size_t)nb * nZ * nE;
+        O.es_day = s; s += (size_t)nb * nA;
+        O.es_night = s; s += (size_t)nb * nZ * nA;
         O.cc_day = s; s += (size_t)nb * nC;
         O.cc_night = s; s += (size_t)nb * nZ * nC;
         O.bg_es = s; s += (size_t)nb * nE;
@@ -576,7 +676,7 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
         auto back = [&](double* dst, const double* src, size_t per_pt) {
             if (dst) CK(cudaMemcpy(dst + b0 * per_pt, src, (size_t)nb * per_pt * sizeof(double), cudaMemcpyDeviceToHost));
         };
-        back(es_day, O.es_day, nE); back(es_night, O.es_night, (size_t)nZ * nE);
+        back(es_day, O.es_day, nA); back(es_night, O.es_night, (size_t)nZ * nA);
         back(cc_day, O.cc_day, nC); back(cc_night, O.cc_night, (size_t)nZ * nC);
         if (mode == kModeRates) { back(bg_es, O.bg_es, nE); back(bg_cc, O.bg_cc, nC); }
     }
@@ -588,6 +688,7 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
 int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad, uint32_t* flags) {
     REQUIRE(params && out_lnl && out_grad, "params, out_lnl and out_grad must not be NULL");
     REQUIRE(h->grad_ok, "binning too large for the gradient kernel's shared-memory tiles");
+    REQUIRE(!h->gen, "the gradient entry serves the exclusive, non-angular analysis only");
     check_data(h, -1);
     const DevTables& T = h->T;
     const int n_dir = 3 + (T.earth_unc ? T.n_layers : 0), n_var = 1 + 2 * n_dir;
@@ -766,6 +867,7 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
                           double* mom_es, double* mom_cc, double* bg_mom_es, double* bg_mom_cc, double* scalars) {
     return guarded(h, [&]() {
         REQUIRE(params && weights, "params and weights must not be NULL");
+        REQUIRE(!h->gen, "derived-mode reductions serve the exclusive, non-angular analysis only");
         REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
         check_data(h, det);
         const DevTables& T = h->T;

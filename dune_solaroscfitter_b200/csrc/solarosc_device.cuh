@@ -47,6 +47,14 @@ struct DevDetector {
     // data stored [1+n_cosz][n_ereco] (row 0 = day) and log(data) alongside
     const double *obs_es, *obs_cc, *logobs_es, *logobs_cc;
     const double2 *ol_es, *ol_cc;         // (m, log m) interleaved, same indexing
+    // ---- inclusive / semi-inclusive / angular branches (solarosc_general.cuh); all zero for the exclusive analysis
+    int incl, ang, n_cos;                 // 0 / 1 inclusive / 2 semi-inclusive; angular ES; cos-scatter bins
+    int cc_out;                           // CC arrays are computed and enter the likelihood (cc_mode && incl != 1)
+    double f_below;                       // CC_split.below on the CC backgrounds (1 unless semi-inclusive)
+    const double *xs8, *xsh;              // CC projected on the ES bins (x f_above), layout of a8
+    const double *yp8, *yph, *yc8, *ych;  // mis-identified ES in the CC bins: matrices (layout of b8) and constants
+    const double *angm, *bgang;           // [n_es][n_cos]: mask_c ES.angular[c][j], BG.angular[c][j]
+    const double2* ol_es_ang;             // angular ES data (m, log m), [1 + n_cosz][n_es][n_cos]
 };
 
 struct DevTables {

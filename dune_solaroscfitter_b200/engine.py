@@ -85,6 +85,16 @@ class SolarOscEngine:
     def _night(self, n, n_ereco):
         return np.empty((n, n_ereco, self.n_cosz) if self.col_major else (n, self.n_cosz, n_ereco))
 
+    def _es_arrays(self, n, det):
+        """ES day / night outputs: with the angular reconstruction they carry the cos-scatter axis in the
+        reference's index order (n_cos, n_ereco[, n_cosz]), reversed when col_major."""
+        nes, nc = self.packed.n_ereco[det][0], self.packed.n_cos[det]
+        if nc == 1:
+            return np.empty((n, nes)), self._night(n, nes)
+        if self.col_major:
+            return np.empty((n, nes, nc)), np.empty((n, self.n_cosz, nes, nc))
+        return np.empty((n, nc, nes)), np.empty((n, nc, nes, self.n_cosz))
+
     # -- API --------------------------------------------------------------------------------------
     def set_data(self, data: Mapping, det: int = 0):
         a = [np.ascontiguousarray(data[k], dtype=np.float64) for k in ("ES_day", "ES_night", "CC_day", "CC_night")]
@@ -117,7 +127,8 @@ class SolarOscEngine:
         p = self._params(params)
         n = len(p)
         nes, ncc = self.packed.n_ereco[det]
-        r = dict(ES_day=np.empty((n, nes)), ES_night=self._night(n, nes), CC_day=np.empty((n, ncc)),
+        es_day, es_night = self._es_arrays(n, det)
+        r = dict(ES_day=es_day, ES_night=es_night, CC_day=np.empty((n, ncc)),
                  CC_night=self._night(n, ncc), BG_ES_tot=np.empty((n, nes)), BG_CC_tot=np.empty((n, ncc)))
         self._check(self._L.solarosc_eval_rates(self._h, det, _dp(p), n, _dp(r["ES_day"]), _dp(r["ES_night"]),
                                                 _dp(r["CC_day"]), _dp(r["CC_night"]), _dp(r["BG_ES_tot"]), _dp(r["BG_CC_tot"])))

@@ -555,3 +555,67 @@ def threshold_index(b_ext: BinSpec, thr: float) -> int:
     if hits.size == 0:
         raise ValueError("threshold exceeds all reco bins")
     return int(hits[0]) + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# inclusive / semi-inclusive / angular tables  (response.jl:111-236)
+# ---------------------------------------------------------------------------------------------
+def hermite_boost(eff: np.ndarray, es_bins: BinSpec) -> np.ndarray:
+    """The temporary high-energy efficiency boost of the inclusive modes: smooth-step from 10 to 12 MeV
+    towards a 90 % plateau (response.jl:147-160,176-179)."""
+    edges = np.linspace(es_bins.min, es_bins.max, es_bins.bin_number + 1)
+    centres = 0.5 * (edges[:-1] + edges[1:])
+    t = np.clip((centres - 0.010) / (0.012 - 0.010), 0.0, 1.0)
+    smooth = t ** 2 * (3 - 2 * t)
+    return eff + smooth * (0.9 - eff)
+
+
+def cc_inclusive_tables(cc_etrue, cc_ereco, cc_mask, etrue: BinSpec, es_bins: BinSpec):
+    """CC events histogrammed in the ES reco binning: response and boosted selection efficiency
+    (response.jl:167-180)."""
+    es_ext = extended_reco_bins(es_bins)
+    resp = create_response_matrix(cc_etrue, cc_ereco, etrue, es_ext)
+    eff = hermite_boost(selection_efficiency(cc_ereco, cc_mask, es_ext), es_bins)
+    return resp, eff
+
+
+def angular_mask(cos_bins: BinSpec, cos_cut: float) -> np.ndarray:
+    """1.0 for cos-scatter bins whose centre is at or above the cut (response.jl:117-120)."""
+    edges = np.linspace(cos_bins.min, cos_bins.max, cos_bins.bin_number + 1)
+    centres = 0.5 * (edges[:-1] + edges[1:])
+    return (centres >= cos_cut).astype(np.float64)
+
+
+def angular_tables(ang_ereco, ang_cos, es_bins: BinSpec, cos_bins: BinSpec, cos_cut: float):
+    """ES.angular (n_cos, n_ereco): P(cos bin | reco bin) from the angular MC; BG.angular: uniform over the
+    allowed bins (response.jl:113-123)."""
+    es_ext = extended_reco_bins(es_bins)
+    r_ang = create_response_matrix(ang_ereco, ang_cos, es_ext, cos_bins).T
+    return (r_ang,) + angular_bg_tables(r_ang.shape, cos_bins, cos_cut)
+
+
+def angular_bg_tables(shape, cos_bins: BinSpec, cos_cut: float):
+    m = angular_mask(cos_bins, cos_cut)
+    r_bg = np.zeros(shape)
+    r_bg[m > 0, :] = 1.0 / np.count_nonzero(m)
+    return r_bg, m
+
+
+def misid_tables(resp_es_nue, resp_es_nuother, r_ang, amask, resp_cc, etrue: BinSpec, es_bins: BinSpec):
+    """Semi-inclusive tables: CC split fractions and the two-step ES -> CC mis-identification responses
+    (response.jl:182-218).  Uses the extended ES edges, whose outer centres are infinite, exactly as the
+    reference does."""
+    n_cos = len(amask)
+    f_above = np.count_nonzero(amask) / n_cos
+    f_below = 1.0 - f_above
+    es_ext = extended_reco_bins(es_bins)
+    with np.errstate(invalid="ignore"):
+        es_centres = 0.5 * (es_ext.bins[:-1] + es_ext.bins[1:])
+    etrue_edges = np.linspace(etrue.min, etrue.max, etrue.bin_number + 1)
+    as_ereco = np.zeros((es_bins.bin_number, resp_cc.shape[1]))
+    for j in range(es_bins.bin_number):
+        b = min(int(np.searchsorted(etrue_edges, es_centres[j], side="right")), etrue.bin_number)   # searchsortedlast
+        if b >= 1:
+            as_ereco[j, :] = resp_cc[b - 1, :]
+    backward = r_ang[amask == 0, :].sum(axis=0)
+    return (resp_es_nue * backward[None, :]) @ as_ereco, (resp_es_nuother * backward[None, :]) @ as_ereco, f_above, f_below

@@ -27,7 +27,8 @@
  *   solarosc_eval_llh_grad the value + gradient BAT's HMC asks of that log-density (mcmc.jl:102-103, where the
  *                          reference differentiates total_llh with ForwardDiff)
  *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
- *                          propagation_main.jl:56-157 (exclusive, non-angular branch)
+ *                          propagation_main.jl:56-157 (all branches: exclusive, inclusive, semi-inclusive,
+ *                          each with or without the angular ES reconstruction)
  *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
  *   solarosc_eval_asymmetry the per-sample D/N asymmetry of derive_variables_from_chain.jl:236-258
  *   solarosc_eval_derived  the replay loop of derive_variables_from_chain.jl:260-444 over a block of chain samples
@@ -50,7 +51,7 @@
 extern "C" {
 #endif
 
-#define SOLAROSC_ABI_VERSION 1
+#define SOLAROSC_ABI_VERSION 2
 #define SOLAROSC_MAX_LAYERS 8   /* Earth layers (the reference's PREM has 6) */
 #define SOLAROSC_MAX_BG 8       /* background components per channel        */
 #define SOLAROSC_N_FIXED_PARAMS 8
@@ -73,6 +74,33 @@ enum {
     SOLAROSC_FLAG_NEG_ERROR = 4u,     /* e <= -1e-3 in some bin (reference errors): lnL = NaN              */
     SOLAROSC_FLAG_NONFINITE = 8u      /* lnL is NaN for another reason                                      */
 };
+
+/*
+ * Optional per-detector tables of the inclusive, semi-inclusive and angular-ES branches
+ * (reference: response.jl:111-236 builds them, propagation_reco.jl:66-199 and propagation_main.jl:98-153 use
+ * them, likelihood_builder.jl:53-78 is the angular likelihood).  2-D arrays follow col_major like the others.
+ *
+ * With angular != 0 every ES array gains the cos-scatter axis, in the reference's index order: ES day is
+ * (n_cos, n_ereco_es), ES night (n_cos, n_ereco_es, n_cosz) -- row-major [c][j] and [c][j][z] when col_major == 0,
+ * [j][c] and [z][j][c] when col_major == 1 -- for obs_es_* and for the es_day / es_night outputs of
+ * solarosc_eval_rates.  solarosc_eval_perbin, solarosc_eval_asymmetry, solarosc_eval_derived and
+ * solarosc_eval_llh_grad serve the exclusive, non-angular branch only and return SOLAROSC_ERR_ARG otherwise.
+ */
+typedef struct solarosc_detector_ext {
+    int32_t inclusive;                  /* 0 exclusive, 1 inclusive_analysis, 2 semi_inclusive_analysis  */
+    int32_t angular;                    /* det_flags.angular_reco                                        */
+    int32_t n_cos;                      /* cos-scatter bins (angular != 0)                               */
+    int32_t reserved;
+    double cc_f_above, cc_f_below;      /* responseMatrices.CC_split (semi-inclusive; response.jl:186-187) */
+    const double *resp_cc_incl;         /* [n_etrue][n_ereco_es] responseMatrices.CC_inclusive (inclusive != 0) */
+    const double *eff_cc_incl;          /* [n_ereco_es]          responseMatrices.eff.CC_incl             */
+    const double *resp_cc_misid_nue;    /* [n_etrue][n_ereco_cc] responseMatrices.CC_misID_nue (inclusive == 2) */
+    const double *resp_cc_misid_nuother;
+    const double *resp_es_angular;      /* [n_cos][n_ereco_es]   responseMatrices.ES.angular (angular != 0) */
+    const double *resp_bg_angular;      /* [n_cos][n_ereco_es]   responseMatrices.BG.angular              */
+    const double *angular_mask;         /* [n_cos] 1.0 where the bin centre >= angular_cos_cut, else 0.0
+                                           (propagation_reco.jl:98-105)                                  */
+} solarosc_detector_ext;
 
 /*
  * Per-detector constant tables (reference: unoscillatedSample.jl:86-116, response.jl:111-141,
@@ -103,6 +131,7 @@ typedef struct solarosc_detector {
     const double *obs_es_night;         /* [n_cosz][n_ereco_es]   */
     const double *obs_cc_day;           /* [n_ereco_cc]           */
     const double *obs_cc_night;         /* [n_cosz][n_ereco_cc]   */
+    const solarosc_detector_ext *ext;   /* NULL: exclusive, non-angular analysis                      */
 } solarosc_detector;
 
 /* Shared constant tables */

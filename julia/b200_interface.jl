@@ -23,10 +23,18 @@ const libb200 = joinpath(@__DIR__, "libsolarosc_b200.so")
 const Handle = Ptr{Cvoid}
 const handle = Ref{Handle}(C_NULL)
 
-const ABI_VERSION = Int32(1)
+const ABI_VERSION = Int32(2)
 const N_FIXED = 8
 
 # ---- C structs (include/solarosc_b200.h) ---------------------------------------------------------
+struct CDetectorExt                      # solarosc_detector_ext: inclusive / semi-inclusive / angular branches
+    inclusive::Int32; angular::Int32; n_cos::Int32; reserved::Int32
+    cc_f_above::Cdouble; cc_f_below::Cdouble
+    resp_cc_incl::Ptr{Cdouble}; eff_cc_incl::Ptr{Cdouble}
+    resp_cc_misid_nue::Ptr{Cdouble}; resp_cc_misid_nuother::Ptr{Cdouble}
+    resp_es_angular::Ptr{Cdouble}; resp_bg_angular::Ptr{Cdouble}; angular_mask::Ptr{Cdouble}
+end
+
 struct CDetector
     es_mode::Int32; cc_mode::Int32
     n_ereco_es::Int32; n_ereco_cc::Int32
@@ -40,6 +48,7 @@ struct CDetector
     raw_bg_es::Ptr{Cdouble}; raw_bg_cc::Ptr{Cdouble}
     bg_es_sides::Ptr{Int32}; bg_es_par::Ptr{Int32}; bg_cc_par::Ptr{Int32}
     obs_es_day::Ptr{Cdouble}; obs_es_night::Ptr{Cdouble}; obs_cc_day::Ptr{Cdouble}; obs_cc_night::Ptr{Cdouble}
+    ext::Ptr{CDetectorExt}
 end
 
 struct CTables
@@ -99,6 +108,24 @@ function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarM
         raw_cc = isempty(bg.CC) ? Float64[] : reduce(vcat, f64.(bg.CC))
         push!(det_names, name)
         push!(n_norms, (count(!=(0), bg.ES_par_counts), count(!=(0), bg.CC_par_counts)))
+        # the other analysis branches of this detector (det_flags of setup.jl:140-150, tables of response.jl:111-236)
+        det = detector_configs[name]
+        ext = Ptr{CDetectorExt}(C_NULL)
+        if det.inclusive_analysis || det.semi_inclusive_analysis || det.angular_reco
+            incl = det.semi_inclusive_analysis ? 2 : (det.inclusive_analysis ? 1 : 0)
+            nul = Ptr{Cdouble}(C_NULL)
+            ncos = r.bins.cos_scatter.bin_number
+            edges = range(r.bins.cos_scatter.min, r.bins.cos_scatter.max, length=ncos + 1)
+            amask = Float64.(0.5 .* (edges[1:end-1] .+ edges[2:end]) .>= det.angular_cos_cut)   # propagation_reco.jl:98-103
+            x = Ref(CDetectorExt(incl, det.angular_reco, det.angular_reco ? ncos : 0, 0,
+                incl == 2 ? r.CC_split.above : 1.0, incl == 2 ? r.CC_split.below : 1.0,
+                incl > 0 ? hold(f64(r.CC_inclusive)) : nul, incl > 0 ? hold(f64(r.eff.CC_incl)) : nul,
+                incl == 2 ? hold(f64(r.CC_misID_nue)) : nul, incl == 2 ? hold(f64(r.CC_misID_nuother)) : nul,
+                det.angular_reco ? hold(f64(r.ES.angular)) : nul, det.angular_reco ? hold(f64(r.BG.angular)) : nul,
+                det.angular_reco ? hold(amask) : nul))
+            push!(keep, x)
+            ext = Base.unsafe_convert(Ptr{CDetectorExt}, x)
+        end
         push!(dets, CDetector(
             li.ES_mode, li.CC_mode, nes, ncc, li.index_ES, li.index_CC,
             hold(f64(u.ES_nue_8B)), hold(f64(u.ES_nuother_8B)), hold(f64(u.CC_8B)),
@@ -107,7 +134,7 @@ function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarM
             hold(f64(r.eff.ES_nue)), hold(f64(r.eff.ES_nuother)), hold(f64(r.eff.CC)),
             length(bg.ES), length(bg.CC), hold(raw_es), hold(raw_cc),
             hold(i32(bg.sides)), hold(i32(bg.ES_par_counts)), hold(i32(bg.CC_par_counts)),
-            hold(f64(obs.ES_day)), hold(f64(obs.ES_night)), hold(f64(obs.CC_day)), hold(f64(obs.CC_night))))
+            hold(f64(obs.ES_day)), hold(f64(obs.ES_night)), hold(f64(obs.CC_day)), hold(f64(obs.CC_night)), ext))
     end
     push!(keep, dets)
 
@@ -242,13 +269,22 @@ arguments are the ones the handle was created from; `precomputed_osc` is accepte
 """
 function propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc=nothing, verbose=false)
     d = findfirst(==(det_flags.det_name), det_names) - 1
-    r = expected_rates_batch([params], d)
-    return r.ES_day[:, 1], r.CC_day[:, 1], r.ES_night[:, :, 1], r.CC_night[:, :, 1], r.BG_ES_tot[:, 1], r.BG_CC_tot[:, 1], nothing
+    nes = resp.bins.ES.bin_number; ncc = resp.bins.CC.bin_number
+    ncos = det_flags.angular_reco ? resp.bins.cos_scatter.bin_number : 1
+    r = expected_rates_batch([params], d; nz=length(exposure_weights), nes=nes, ncc=ncc, ncos=ncos)
+    ES_day   = ncos > 1 ? r.ES_day[:, :, 1]      : r.ES_day[:, 1]
+    ES_night = ncos > 1 ? r.ES_night[:, :, :, 1] : r.ES_night[:, :, 1]
+    # CC_incl_spectrum (7th element, informational: setup.jl:235-243) is the CC part of the ES arrays, i.e. the
+    # difference to the exclusive rates of the same point; the engine does not return it separately
+    return ES_day, r.CC_day[:, 1], ES_night, r.CC_night[:, :, 1], r.BG_ES_tot[:, 1], r.BG_CC_tot[:, 1], nothing
 end
 
-function expected_rates_batch(params, det::Int=0; nz::Int, nes::Int, ncc::Int)
+# Rate arrays of a batch, shaped like the reference's with the batch index last: ES_day (nes, B) or, with the
+# angular reconstruction, (ncos, nes, B); ES_night (nz, nes, B) or (ncos, nes, nz, B).
+function expected_rates_batch(params, det::Int=0; nz::Int, nes::Int, ncc::Int, ncos::Int=1)
     M = pack_many(params); B = size(M, 2)
-    ES_day = Array{Float64}(undef, nes, B); ES_night = Array{Float64}(undef, nz, nes, B)
+    ES_day   = ncos > 1 ? Array{Float64}(undef, ncos, nes, B)     : Array{Float64}(undef, nes, B)
+    ES_night = ncos > 1 ? Array{Float64}(undef, ncos, nes, nz, B) : Array{Float64}(undef, nz, nes, B)
     CC_day = Array{Float64}(undef, ncc, B); CC_night = Array{Float64}(undef, nz, ncc, B)
     BG_ES = Array{Float64}(undef, nes, B);  BG_CC = Array{Float64}(undef, ncc, B)
     GC.@preserve M ES_day ES_night CC_day CC_night BG_ES BG_CC begin

@@ -267,30 +267,82 @@ def normalize_backgrounds(t, pv: ParamView):
     return bg_es, bg_cc
 
 
+def _flag(t, key) -> int:
+    return int(t[key]) if key in t else 0
+
+
 def propagate_samples(p, t, fast=True, earth_uncertainty=True, precomputed_osc=None, es_mode=True, cc_mode=True):
-    """Exclusive, non-angular branch of propagateSamples (propagation_main.jl:56-157)."""
+    """propagateSamples (propagation_main.jl:56-157), all branches.  The optional table keys `inclusive`
+    (0 exclusive, 1 inclusive, 2 semi-inclusive) and `angular` select them; with `angular` the ES arrays are
+    (n_cos, n_ereco) and (n_cos, n_ereco, n_cosz) as in the reference."""
     pv = view(p, t)
     osc = precomputed_osc if precomputed_osc is not None else compute_shared_osc_probs(p, t, fast, earth_uncertainty)
     bg_es, bg_cc = normalize_backgrounds(t, pv)
     es, cc = compute_oscillated_samples(t, pv, osc)
-    wz = t["exposure_weights"][:, None]
-    nz = len(t["exposure_weights"])
-    if es_mode:   # propagation_reco.jl:10-29
+    w = np.asarray(t["exposure_weights"])
+    wz = w[:, None]
+    nz = len(w)
+    incl, ang = _flag(t, "inclusive"), _flag(t, "angular")
+    n_es = len(bg_es)
+    if ang:
+        ncos = int(t["n_cos"])
+        r_ang, r_bg, amask = np.asarray(t["resp_es_angular"]), np.asarray(t["resp_bg_angular"]), np.asarray(t["angular_mask"])
+    if es_mode:
         ne_d = apply_day_response(es["nue_day"], t["resp_es_nue"], t["eff_es_nue"])
         ne_n = apply_night_response(es["nue_night"], t["resp_es_nue"], t["eff_es_nue"])
         no_d = apply_day_response(es["nuother_day"], t["resp_es_nuother"], t["eff_es_nuother"])
         no_n = apply_night_response(es["nuother_night"], t["resp_es_nuother"], t["eff_es_nuother"])
-        es_day = (ne_d + no_d) + 0.5 * bg_es
-        es_night = (ne_n + no_n) + 0.5 * (bg_es[None, :] * wz)
+        if ang:   # compute_ES_angular_event_rates, propagation_reco.jl:66-108
+            sig_d, sig_n = ne_d + no_d, ne_n + no_n
+            es_day = r_ang * sig_d[None, :] + r_bg * bg_es[None, :] * 0.5
+            es_night = r_ang[:, :, None] * sig_n.T[None, :, :] + (r_bg[:, :, None] * (bg_es[:, None] * w[None, :])[None, :, :]) * 0.5
+            es_day = es_day * amask[:, None]
+            es_night = es_night * amask[:, None, None]
+        else:     # compute_ES_event_rates, propagation_reco.jl:10-29
+            es_day = (ne_d + no_d) + 0.5 * bg_es
+            es_night = (ne_n + no_n) + 0.5 * (bg_es[None, :] * wz)
     else:
-        es_day, es_night = np.zeros(len(bg_es)), np.zeros((nz, len(bg_es)))
-    if cc_mode:   # propagation_reco.jl:117-130
-        cc_day = apply_day_response(cc["day"], t["resp_cc"], t["eff_cc"]) + 0.5 * bg_cc
-        cc_night = apply_night_response(cc["night"], t["resp_cc"], t["eff_cc"]) + 0.5 * (bg_cc[None, :] * wz)
-    else:
+        es_day, es_night = (np.zeros((ncos, n_es)), np.zeros((ncos, n_es, nz))) if ang else (np.zeros(n_es), np.zeros((nz, n_es)))
+
+    def cc_exclusive():   # compute_CC_event_rates, propagation_reco.jl:117-130
+        if not cc_mode:
+            return np.zeros(len(bg_cc)), np.zeros((nz, len(bg_cc)))
+        return (apply_day_response(cc["day"], t["resp_cc"], t["eff_cc"]) + 0.5 * bg_cc,
+                apply_night_response(cc["night"], t["resp_cc"], t["eff_cc"]) + 0.5 * (bg_cc[None, :] * wz))
+
+    def cc_inclusive():   # compute_CC_inclusive_event_rates, propagation_reco.jl:139-170
+        if not cc_mode:
+            return (np.zeros((ncos, n_es)), np.zeros((ncos, n_es, nz))) if ang else (np.zeros(n_es), np.zeros((nz, n_es)))
+        d = apply_day_response(cc["day"], t["resp_cc_incl"], t["eff_cc_incl"])
+        n = apply_night_response(cc["night"], t["resp_cc_incl"], t["eff_cc_incl"])
+        if ang:
+            return r_bg * d[None, :], r_bg[:, :, None] * n.T[None, :, :]
+        return d, n
+
+    incl_spectrum = None
+    if incl == 2:         # propagation_main.jl:109-137
+        f_above, f_below = float(t["cc_f_above"]), float(t["cc_f_below"])
+        ci_d, ci_n = cc_inclusive()
+        incl_spectrum = f_above * ((ci_d.sum(axis=0) + ci_n.sum(axis=(0, 2))) if ang else (ci_d + ci_n.sum(axis=0)))
+        es_day = es_day + f_above * ci_d
+        es_night = es_night + f_above * ci_n
+        cc_day, cc_night = cc_exclusive()
+        cc_day, cc_night = cc_day * f_below, cc_night * f_below
+        if es_mode:       # compute_ES_misID_CC_event_rates, propagation_reco.jl:187-199
+            cc_day = cc_day + (apply_day_response(es["nue_day"], t["resp_cc_misid_nue"], t["eff_cc"]) +
+                               apply_day_response(es["nuother_day"], t["resp_cc_misid_nuother"], t["eff_cc"]))
+            cc_night = cc_night + (apply_night_response(es["nue_night"], t["resp_cc_misid_nue"], t["eff_cc"]) +
+                                   apply_night_response(es["nuother_night"], t["resp_cc_misid_nuother"], t["eff_cc"]))
+    elif incl == 1:       # propagation_main.jl:139-150
+        ci_d, ci_n = cc_inclusive()
+        incl_spectrum = (ci_d.sum(axis=0) + ci_n.sum(axis=(0, 2))) if ang else (ci_d + ci_n.sum(axis=0))
+        es_day = es_day + ci_d
+        es_night = es_night + ci_n
         cc_day, cc_night = np.zeros(len(bg_cc)), np.zeros((nz, len(bg_cc)))
+    else:
+        cc_day, cc_night = cc_exclusive()
     return dict(ES_day=es_day, CC_day=cc_day, ES_night=es_night, CC_night=cc_night,
-                BG_ES_tot=bg_es, BG_CC_tot=bg_cc)
+                BG_ES_tot=bg_es, BG_CC_tot=bg_cc, CC_incl_spectrum=incl_spectrum)
 
 
 # ---------------------------------------------------------------------------
@@ -342,15 +394,30 @@ def llh_channel(rates_day, rates_night, obs_day, obs_night, idx: int, flags=None
     return out
 
 
+def llh_es_angle(rates_day, rates_night, obs_day, obs_night, idx: int, flags=None) -> float:
+    """llh_ES_angle (likelihood_builder.jl:53-78): day (n_cos, n_E) and every night slice (n_cos, n_E, n_cosz),
+    energy bins idx:end, all cos-scatter bins."""
+    k = idx - 1
+    out = poisson_log_likelihood(rates_day[:, k:].ravel(), obs_day[:, k:].ravel(), flags)
+    for z in range(rates_night.shape[2]):
+        out += poisson_log_likelihood(rates_night[:, k:, z].ravel(), obs_night[:, k:, z].ravel(), flags)
+    return out
+
+
 def total_llh(p, t, data, fast=True, earth_uncertainty=True, use_es=True, use_cc=True,
-              precomputed_osc=None) -> float:
-    """likelihood_main.jl:30-35 + likelihood_builder.jl:216-259 for one detector."""
+              precomputed_osc=None, es_mode=True, cc_mode=True) -> float:
+    """likelihood_main.jl:8-35 + likelihood_builder.jl:216-259 for one detector: use_ES = ES_mode,
+    use_CC = CC_mode && (!inclusive || semi_inclusive), llh_ES_angle when angular."""
     pv = view(p, t)
     if earth_uncertainty and not check_earth_norm_bounds(pv):
         return -math.inf
-    r = propagate_samples(p, t, fast, earth_uncertainty, precomputed_osc)
+    r = propagate_samples(p, t, fast, earth_uncertainty, precomputed_osc, es_mode, cc_mode)
     llh = 0.0
-    if use_es:
+    use_es = use_es and es_mode
+    use_cc = use_cc and cc_mode and _flag(t, "inclusive") != 1
+    if use_es and _flag(t, "angular"):
+        llh += llh_es_angle(r["ES_day"], r["ES_night"], data["ES_day"], data["ES_night"], int(t["index_es"]))
+    elif use_es:
         llh += llh_channel(r["ES_day"], r["ES_night"], data["ES_day"], data["ES_night"], int(t["index_es"]))
     if use_cc:
         llh += llh_channel(r["CC_day"], r["CC_night"], data["CC_day"], data["CC_night"], int(t["index_cc"]))

@@ -20,6 +20,25 @@ def tables():
     return dict(np.load(os.path.join(GOLDEN, "tables_escc.npz")))
 
 
+def branch_tables(tables, inclusive=0, angular=0):
+    """Measurement tables switched to another analysis branch (VD block of config.yaml:123-156): the extra
+    tables of tests/golden/tables_ext.npz merged in, the ES efficiencies boosted as response.jl:147-160 does for
+    the inclusive modes."""
+    ext = dict(np.load(os.path.join(GOLDEN, "tables_ext.npz")))
+    t = dict(tables)
+    t.update({k: ext[k] for k in ("n_cos", "resp_cc_incl", "eff_cc_incl", "resp_es_angular", "resp_bg_angular", "angular_mask",
+                                  "resp_cc_misid_nue", "resp_cc_misid_nuother", "cc_f_above", "cc_f_below")})
+    if inclusive:
+        t["eff_es_nue"], t["eff_es_nuother"] = ext["eff_es_nue_boosted"], ext["eff_es_nuother_boosted"]
+    t["inclusive"], t["angular"] = np.int32(inclusive), np.int32(angular)
+    return t
+
+
+@pytest.fixture(scope="session")
+def branches():
+    return branch_tables
+
+
 @pytest.fixture(scope="session")
 def asimov(tables):
     from oracle import oracle_np

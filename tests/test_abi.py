@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.solarosc_abi_version() == abi.ABI_VERSION == 1
+    assert lib.solarosc_abi_version() == abi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -42,14 +42,16 @@ def test_struct_layouts_match_the_header(tmp_path):
     if cc is None:
         pytest.skip("no C compiler")
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
                    'sizeof(solarosc_detector),sizeof(solarosc_tables),sizeof(solarosc_config),'
-                   'offsetof(solarosc_tables,det),offsetof(solarosc_detector,obs_cc_night));return 0;}\n' % HEADER)
+                   'offsetof(solarosc_tables,det),offsetof(solarosc_detector,obs_cc_night),sizeof(solarosc_detector_ext),'
+                   'offsetof(solarosc_detector,ext),offsetof(solarosc_detector_ext,angular_mask));return 0;}\n' % HEADER)
     exe = tmp_path / "sz"
     subprocess.run([cc, str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert got == [C.sizeof(abi.Detector), C.sizeof(abi.Tables), C.sizeof(abi.Config),
-                   abi.Tables.det.offset, abi.Detector.obs_cc_night.offset]
+                   abi.Tables.det.offset, abi.Detector.obs_cc_night.offset, C.sizeof(abi.DetectorExt),
+                   abi.Detector.ext.offset, abi.DetectorExt.angular_mask.offset]
 
 
 def test_create_rejects_bad_arguments_without_a_gpu(lib, tables):

@@ -1,0 +1,116 @@
+"""Inclusive, semi-inclusive and angular-ES branches of propagateSamples (propagation_main.jl:98-153,
+propagation_reco.jl:66-199) and llh_ES_angle (likelihood_builder.jl:53-78).
+
+CPU part: structural identities of the oracle's restatement.  GPU part: the general fold (gen_kernel) against the
+oracle through the C ABI, every branch combination."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+
+
+def _truth(t):
+    return np.asarray(t["truth"], dtype=float)
+
+
+def test_angular_rates_sum_back_to_the_energy_spectrum(tables, branches):
+    """ES.angular and BG.angular columns sum to one over the cos bins, so without a cut the angular arrays summed
+    over cos theta are the non-angular rates (propagation_reco.jl:86-96 vs :10-29)."""
+    t = branches(tables, 0, 1)
+    t["angular_mask"] = np.ones_like(t["angular_mask"])
+    t["resp_bg_angular"] = np.full_like(t["resp_bg_angular"], 1.0 / int(t["n_cos"]))
+    a = O.propagate_samples(_truth(t), t)
+    b = O.propagate_samples(_truth(tables), tables)
+    assert a["ES_day"].shape == (25, 30) and a["ES_night"].shape == (25, 30, 50)
+    assert np.allclose(a["ES_day"].sum(axis=0), b["ES_day"], rtol=1e-12)
+    assert np.allclose(a["ES_night"].sum(axis=0).T, b["ES_night"], rtol=1e-12)
+    assert np.array_equal(a["CC_night"], b["CC_night"])
+
+
+def test_angular_cut_zeroes_the_backward_bins(tables, branches):
+    t = branches(tables, 0, 1)
+    r = O.propagate_samples(_truth(t), t)
+    back = t["angular_mask"] == 0
+    assert back.sum() == 12 and np.all(r["ES_day"][back] == 0) and np.all(r["ES_night"][back] == 0)
+    assert np.all(r["ES_day"][~back][:, 4:] > 0)          # (the efficiency is zero in the lowest reco bins)
+
+
+def test_inclusive_moves_cc_into_the_es_bins(tables, branches):
+    t = branches(tables, 1, 0)
+    r = O.propagate_samples(_truth(t), t)
+    assert np.all(r["CC_day"] == 0) and np.all(r["CC_night"] == 0)
+    t0 = dict(t); t0["inclusive"] = np.int32(0)
+    e = O.propagate_samples(_truth(t0), t0)
+    extra = r["ES_day"] - e["ES_day"]
+    assert np.all(extra >= 0) and extra.sum() > 0
+    assert np.allclose(r["CC_incl_spectrum"], extra + (r["ES_night"] - e["ES_night"]).sum(axis=0), rtol=1e-9)
+    # use_CC is false in the inclusive analysis (likelihood_main.jl:12): the CC data never enter
+    d = {k: r[k] for k in ("ES_day", "ES_night", "CC_day", "CC_night")}
+    assert O.total_llh(_truth(t), t, d) == O.total_llh(_truth(t), t, {**d, "CC_day": d["CC_day"] + 5.0})
+
+
+def test_semi_inclusive_splits_cc_between_the_hemispheres(tables, branches):
+    t = branches(tables, 2, 0)
+    r = O.propagate_samples(_truth(t), t)
+    t0 = dict(t); t0["inclusive"] = np.int32(0)
+    e = O.propagate_samples(_truth(t0), t0)
+    t1 = dict(t); t1["inclusive"] = np.int32(1)
+    i = O.propagate_samples(_truth(t1), t1)
+    fa, fb = float(t["cc_f_above"]), float(t["cc_f_below"])
+    assert abs(fa + fb - 1) < 1e-15
+    assert np.allclose(r["ES_day"] - e["ES_day"], fa * (i["ES_day"] - e["ES_day"]), rtol=1e-9, atol=1e-12)
+    misid = r["CC_day"] - fb * e["CC_day"]
+    assert np.all(misid >= -1e-12) and misid.sum() > 0      # backward-scattered ES read as CC
+
+
+# ---- GPU parity ------------------------------------------------------------------------------------------------------
+BRANCHES = [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("incl,ang", BRANCHES)
+def test_general_fold_matches_the_oracle(tables, branches, draw, incl, ang):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    t = branches(tables, incl, ang)
+    data = O.asimov_data(t)
+    p = draw(tables, 6, seed=300 + 10 * incl + ang)
+    with SolarOscEngine(t, data=data) as e:
+        got = e.eval_rates(p)
+        lnl = e.eval_llh(p)
+        many = e.eval_llh(np.tile(p, (60, 1)))          # several chunks' worth of CTAs
+    for i in range(len(p)):
+        ref = O.propagate_samples(p[i], t)
+        for k in ("ES_day", "ES_night", "CC_day", "CC_night", "BG_ES_tot", "BG_CC_tot"):
+            a, b = got[k][i], ref[k]
+            assert a.shape == b.shape, (k, a.shape, b.shape)
+            scale = np.maximum(np.abs(b), 1e-9 * np.max(np.abs(b)))
+            assert np.max(np.abs(a - b) / np.where(scale > 0, scale, 1.0)) < 1e-9, k     # BASELINE.json: rates <= 1e-9 relative
+        assert abs(2 * lnl[i] - 2 * O.total_llh(p[i], t, data)) < 1e-6                  # and -2lnL <= 1e-6 absolute
+    assert np.array_equal(many.reshape(60, -1), np.tile(lnl, (60, 1)))
+
+
+@pytest.mark.gpu
+def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw):
+    from dune_solaroscfitter_b200.engine import SolarOscEngine, SolarOscError
+    t = branches(tables, 1, 1)
+    data = O.asimov_data(t)
+    p = draw(tables, 3, seed=77)
+    with SolarOscEngine(t, data=data) as e:
+        a = e.eval_rates(p)
+        la = e.eval_llh(p)
+        with pytest.raises(SolarOscError):
+            e.eval_perbin(p)
+        with pytest.raises(SolarOscError):
+            e.eval_llh_grad(p)
+    # the same tables and data as Julia lays them out (column-major: numpy views with reversed shapes)
+    tj = dict(t)
+    for k in ("resp_es_nue", "resp_es_nuother", "resp_cc", "resp_cc_incl", "resp_es_angular", "resp_bg_angular"):
+        tj[k] = np.ascontiguousarray(np.asarray(t[k]).T)
+    dj = {k: np.ascontiguousarray(np.transpose(v)) for k, v in data.items()}
+    with SolarOscEngine(tj, data=dj, col_major=True) as e:
+        b = e.eval_rates(p)
+        lb = e.eval_llh(p)
+    assert np.array_equal(la, lb)
+    assert np.array_equal(b["ES_day"], np.transpose(a["ES_day"], (0, 2, 1)))
+    assert np.array_equal(b["ES_night"], np.transpose(a["ES_night"], (0, 3, 2, 1)))
+    assert np.array_equal(b["CC_night"], np.transpose(a["CC_night"], (0, 2, 1)))
