@@ -287,7 +287,24 @@ def main():
             eng.eval_llh_grad(gp)
         grad_value = 3 * len(gp) / (time.perf_counter() - t0)
 
+    # ---- the other analysis branches (VD block of config.yaml: inclusive + angular ES, 25 cos-scatter bins) ----------
+    branch_value = None
+    if rank == 0:
+        ext = dict(np.load(os.path.join(ROOT, "tests", "golden", "tables_ext.npz")))
+        tv = dict(t)
+        tv.update({k: ext[k] for k in ("n_cos", "resp_cc_incl", "eff_cc_incl", "resp_es_angular", "resp_bg_angular", "angular_mask")})
+        tv["eff_es_nue"], tv["eff_es_nuother"] = ext["eff_es_nue_boosted"], ext["eff_es_nuother_boosted"]
+        tv["inclusive"], tv["angular"] = np.int32(1), np.int32(1)
+        bp = np.ascontiguousarray(params[:: max(1, n // 32768)][:32768])
+        with SolarOscEngine(tv, data=oracle_np.asimov_data(tv), device=local) as ev:
+            ev.eval_llh(bp)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ev.eval_llh(bp)
+            branch_value = 2 * len(bp) / (time.perf_counter() - t0)
+
     # ---- parity gate on this run's own output ------------------------------------------------------------
+    step_device()                              # (the grouped pass left its own summation order in d_lnl)
     torch.cuda.synchronize()
     lnl_dev = d_lnl.cpu().numpy()
     same = bool(np.array_equal(lnl_dev, out_np))
@@ -304,12 +321,21 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per point x points per launch)
+    traffic, pts_per_launch = None, n * args.steps / max(1, launches)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_llh_kernel_traffic.json")))
+        traffic = tr["dram_bytes_per_point"] * pts_per_launch
+    except Exception:
+        pass
     osc_s = ms_osc * 1e-3 / args.steps         # average duration of the first kernel's launches of one step
     rates_s = ms_rates * 1e-3 / args.steps
     if fused:   # one kernel does K1..K5
         ach = n * (FLOP_OSC + FLOP_RATES) / osc_s * 1e-12
         roofline = {"bound": "fp64", "kernel": "llh_kernel (fused K1-K5)", "achieved": ach, "peak": fp64_peak,
-                    "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                    "traffic_note": "DRAM bytes per launch: ncu dram__bytes_read+write per point (profiles/r01_llh_kernel_traffic.json) "
+                                    f"x {pts_per_launch:.0f} points per launch; algorithmic bytes are 164 per point",
                     "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                     "ms_per_step": ms_osc / args.steps, "share_of_step": 1.0,
                     "sincos_per_s": n * SINCOS_PER_EVAL / osc_s,
@@ -344,6 +370,9 @@ def main():
         "value_and_gradient": {"value": grad_value, "unit": "lnL + gradient evaluations/s", "batch": 4096,
                                "note": "solarosc_eval_llh_grad from host buffers on one GPU (HMC entry, C3); every evaluation "
                                        "runs 1 + 2 x 9 oscillation stages; not the headline"},
+        "inclusive_angular": {"value": branch_value, "unit": UNIT, "batch": 32768,
+                              "note": "VD-style analysis (inclusive CC + angular ES, 25 cos-scatter bins: 25 x the Poisson terms) through "
+                                      "solarosc_eval_llh from host buffers (osc_kernel + gen_kernel); not the headline"},
         "gpu_launches": int(launches), "clocks": clocks,
         "e2e_equals_device_result": same,
     }
