@@ -14,7 +14,7 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_grad.cuh", "solarosc_batcher.hpp")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_grad.cuh", "solarosc_general.cuh", "solarosc_setup.cuh", "solarosc_batcher.hpp")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (
@@ -24,6 +24,8 @@ EXPORTS = (
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
     "solarosc_batcher_create", "solarosc_batcher_create_with", "solarosc_batcher_eval", "solarosc_batcher_leave",
     "solarosc_batcher_stats", "solarosc_batcher_destroy",
+    "solarosc_setup_bin_index", "solarosc_setup_bin_index_device", "solarosc_setup_histogram",
+    "solarosc_setup_response_matrix", "solarosc_setup_earth_paths",
 )
 
 BATCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -73,6 +75,13 @@ def load():
     L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_asymmetry.argtypes = [H, C.c_int, dp, sz, dp, dp]
     L.solarosc_eval_derived.argtypes = [H, C.c_int, dp, sz] + [dp] * 11
+    ip, u8 = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    L.solarosc_setup_bin_index.argtypes = [dp, sz, dp, sz, ip]
+    L.solarosc_setup_bin_index_device.argtypes = [H, dp, sz, dp, sz, ip]
+    L.solarosc_setup_histogram.argtypes = [dp, dp, u8, sz, C.c_int32, C.c_double, C.c_double, dp, C.c_int32, dp]
+    L.solarosc_setup_response_matrix.argtypes = [dp, dp, sz, C.c_int32, C.c_double, C.c_double, dp, C.c_int32, C.c_double,
+                                                 C.c_double, dp, dp, ip, ip]
+    L.solarosc_setup_earth_paths.argtypes = [dp, dp, sz, dp, sz, C.c_int32, ip, ip, dp, sz, dp, ip]
     L.solarosc_eval_oscprobs.argtypes = [H, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_p1e.argtypes = [H, dp, sz, dp]
     L.solarosc_eval_llh_device.argtypes = [H, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, C.c_void_p]

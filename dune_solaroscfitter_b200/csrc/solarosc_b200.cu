@@ -16,6 +16,7 @@
 
 #include "solarosc_grad.cuh"
 #include "solarosc_general.cuh"
+#include "solarosc_setup.cuh"
 
 using namespace solarosc;
 
@@ -1125,6 +1126,91 @@ int solarosc_measure_fp64_peak(solarosc_handle* h, double* tflops) {
         *tflops = fl / (best * 1e-3) * 1e-12;
         return (int)SOLAROSC_OK;
     });
+}
+
+}  // extern "C"
+
+// ---- set-up stage (solarosc_setup.cuh) ----------------------------------------------------------------------------
+extern "C" {
+
+int solarosc_setup_bin_index(const double* edges, size_t n_edges, const double* v, size_t n, int32_t* out) {
+    if (!edges || n_edges == 0 || (n && (!v || !out))) return SOLAROSC_ERR_ARG;
+    for (size_t i = 0; i < n; ++i) out[i] = solarosc_setup::search_last(edges, (int)n_edges, v[i]);
+    return SOLAROSC_OK;
+}
+
+int solarosc_setup_bin_index_device(solarosc_handle* h, const double* edges, size_t n_edges, const double* v, size_t n, int32_t* out) {
+    return guarded(h, [&]() {
+        REQUIRE(edges && n_edges > 0 && n_edges <= 4096 && (n == 0 || (v && out)), "bad arguments");
+        if (n == 0) return (int)SOLAROSC_OK;
+        double *d_e = nullptr, *d_v = nullptr;
+        int32_t* d_o = nullptr;
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_e), n_edges * sizeof(double)));
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_v), n * sizeof(double)));
+        CK(cudaMalloc(reinterpret_cast<void**>(&d_o), n * sizeof(int32_t)));
+        CK(cudaMemcpyAsync(d_e, edges, n_edges * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d_v, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+        solarosc_setup::bin_index_kernel<<<grid, 256, n_edges * sizeof(double), h->stream>>>(d_e, (int)n_edges, d_v, n, d_o);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, d_o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(d_e); cudaFree(d_v); cudaFree(d_o);
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_setup_histogram(const double* v, const double* w, const uint8_t* keep, size_t n, int32_t n_bins, double lo, double hi,
+                             const double* edges, int32_t normalise, double* out) {
+    if (n_bins <= 0 || !out || (n && !v)) return SOLAROSC_ERR_ARG;
+    try {
+        solarosc_setup::histogram(v, w, keep, n, solarosc_setup::make_bins(n_bins, lo, hi, edges), normalise != 0, out);
+    } catch (...) { return SOLAROSC_ERR_ALLOC; }
+    return SOLAROSC_OK;
+}
+
+int solarosc_setup_response_matrix(const double* x, const double* y, size_t n, int32_t nbx, double xlo, double xhi,
+                                   const double* xedges, int32_t nby, double ylo, double yhi, const double* yedges, double* out,
+                                   int32_t* xi, int32_t* yi) {
+    if (nbx <= 0 || nby <= 0 || !out || (n && (!x || !y))) return SOLAROSC_ERR_ARG;
+    try {
+        solarosc_setup::response_matrix(x, y, n, solarosc_setup::make_bins(nbx, xlo, xhi, xedges),
+                                        solarosc_setup::make_bins(nby, ylo, yhi, yedges), out, xi, yi);
+    } catch (...) { return SOLAROSC_ERR_ALLOC; }
+    return SOLAROSC_OK;
+}
+
+int solarosc_setup_earth_paths(const double* radius, const double* potential, size_t n_model, const double* cosz, size_t n_paths,
+                               int32_t n_layers_expected, int32_t* seg_start, int32_t* seg_layer, double* seg_length,
+                               size_t seg_capacity, double* lookup, int32_t* n_layers_found) {
+    if (!radius || !potential || n_model < 2 || !cosz || !seg_start || !seg_layer || !seg_length) return SOLAROSC_ERR_ARG;
+    try {
+        solarosc_setup::PathBuilder pb;
+        if (!pb.init(radius, potential, n_model)) return SOLAROSC_ERR_ARG;
+        if (n_layers_found) *n_layers_found = (int32_t)pb.layers.size();
+        if (n_layers_expected > 0 && (int)pb.layers.size() != n_layers_expected) return SOLAROSC_ERR_ARG;
+        std::vector<std::vector<solarosc_setup::Segment>> paths(n_paths);
+        size_t total = 0;
+        seg_start[0] = 0;
+        for (size_t p = 0; p < n_paths; ++p) {
+            if (!pb.path(cosz[p], paths[p])) return SOLAROSC_ERR_ARG;
+            if (total + paths[p].size() > seg_capacity) return SOLAROSC_ERR_ARG;
+            for (const auto& sg : paths[p]) { seg_layer[total] = sg.index; seg_length[total] = sg.length; ++total; }
+            seg_start[p + 1] = (int32_t)total;
+        }
+        if (lookup) {   // earth_lookup padded from the vertical path (setup.jl:52-66)
+            std::vector<double> base = solarosc_setup::avg_densities(paths);
+            const size_t n_exp = n_layers_expected > 0 ? (size_t)n_layers_expected : base.size();
+            if (base.size() < n_exp) {
+                std::vector<std::vector<solarosc_setup::Segment>> vert(1);
+                if (!pb.path(-1.0, vert[0])) return SOLAROSC_ERR_ARG;
+                const std::vector<double> ref = solarosc_setup::avg_densities(vert);
+                for (size_t k = base.size(); k < n_exp && k < ref.size(); ++k) base.push_back(ref[k]);
+            }
+            for (size_t k = 0; k < base.size(); ++k) lookup[k] = base[k];
+        }
+    } catch (...) { return SOLAROSC_ERR_ALLOC; }
+    return SOLAROSC_OK;
 }
 
 }  // extern "C"

@@ -293,6 +293,35 @@ int solarosc_last_fused(const solarosc_handle *h);
  * denominator of the FP64 roofline, which MEASURED_PEAKS.json does not carry. */
 int solarosc_measure_fp64_peak(solarosc_handle *h, double *tflops);
 
+/*
+ * Set-up stage: the constant tables solarosc_create consumes, built from the MC samples and the Earth model the way
+ * the reference's Julia set-up does (response.jl:3-141, backgrounds.jl:37-140, histHelpers.jl:11-78,
+ * makePaths.jl:48-294, setup.jl:52-66).  Host functions (one-time work); integer bin indices are bit-exact
+ * (left-closed bins, searchsortedlast), weights are summed in file order.  edges == NULL means n_bins equal bins on
+ * [lo, hi]; otherwise n_bins + 1 explicit edges (the reference pushes the outer reco edges to -Inf / +Inf while
+ * still testing the range [lo, hi], response.jl:47 vs :98-104).
+ *
+ *   solarosc_setup_bin_index         out[i] = searchsortedlast(edges, v[i]) (0 below the first edge)
+ *   solarosc_setup_bin_index_device  the same on the GPU of handle h (one thread per event), host buffers
+ *   solarosc_setup_histogram         create_histogram: keep (NULL = all) selects events, w (NULL = 1) weighs them
+ *   solarosc_setup_response_matrix   create_response_matrix: out [nbx][nby] row-normalised; xi / yi (optional) receive
+ *                                    every event's 1-based (true, reco) bin, 0 for events outside the range
+ *   solarosc_setup_earth_paths       make_potential_for_integrand + get_avg_densities for the given zenith cosines:
+ *                                    CSR segment tables (layer ids 1-based, detector -> far surface) and the mean
+ *                                    potential per layer (lookup, at least n_layers_expected entries)
+ */
+int solarosc_setup_bin_index(const double *edges, size_t n_edges, const double *v, size_t n, int32_t *out);
+int solarosc_setup_bin_index_device(solarosc_handle *h, const double *edges, size_t n_edges, const double *v, size_t n,
+                                    int32_t *out);
+int solarosc_setup_histogram(const double *v, const double *w, const uint8_t *keep, size_t n, int32_t n_bins, double lo,
+                             double hi, const double *edges, int32_t normalise, double *out);
+int solarosc_setup_response_matrix(const double *x, const double *y, size_t n, int32_t nbx, double xlo, double xhi,
+                                   const double *xedges, int32_t nby, double ylo, double yhi, const double *yedges,
+                                   double *out, int32_t *xi, int32_t *yi);
+int solarosc_setup_earth_paths(const double *radius, const double *potential, size_t n_model, const double *cosz,
+                               size_t n_paths, int32_t n_layers_expected, int32_t *seg_start, int32_t *seg_layer,
+                               double *seg_length, size_t seg_capacity, double *lookup, int32_t *n_layers_found);
+
 #ifdef __cplusplus
 }
 #endif
