@@ -232,6 +232,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         }
         row_cost[pth / T.n_sub] += n;
     }
+    T.n_ltbl = 1 + *std::max_element(app_layer.begin(), app_layer.end());
     std::vector<Seg> seg(n_seg);
     for (int i = 0; i < n_seg; ++i) seg[i] = Seg{app_len[i], app_layer[i], 0};
     T.seg = h->upload(seg.data(), n_seg);
@@ -465,10 +466,10 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         if (const char* e = std::getenv("SOLAROSC_LLH_CHUNKS")) chunks = std::max(1, atoi(e));
         else
             while (chunks < T.n_etrue &&
-                   llh_smem_bytes(T.n_layers, (T.n_etrue + chunks - 1) / chunks, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double)) > budget)
+                   llh_smem_bytes(T.n_ltbl, (T.n_etrue + chunks - 1) / chunks, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double)) > budget)
                 ++chunks;
         h->fused_cb = (T.n_etrue + chunks - 1) / chunks;
-        h->fused_smem = llh_smem_bytes(T.n_layers, h->fused_cb, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double));
+        h->fused_smem = llh_smem_bytes(T.n_ltbl, h->fused_cb, T.n_etrue, T.n_cosz, h->max_ereco, h->seg_bytes / sizeof(double));
         h->fused_seg = true;
         if (const char* e = std::getenv("SOLAROSC_LLH_EXTRA_SMEM")) h->fused_smem += (size_t)atoi(e);   // diagnostics: force fewer CTAs per SM
         h->fused_ok = h->fused_seg && h->fused_smem <= per_cta_max;   // the fused kernel reads the path tables from shared memory
@@ -490,14 +491,14 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     const DevTables& T = h->T;
     // coarse bins per CTA: the whole spectrum when the batch alone fills the GPU, otherwise split the
     // energy axis so that about two CTAs per SM exist; never more than shared memory holds
-    const size_t per_cb = osc_smem_bytes(T.n_layers, 1);
+    const size_t per_cb = osc_smem_bytes(T.n_ltbl, 1);
     const int cb_max = (int)std::max<size_t>(1, h->osc_smem_limit / per_cb);
     int want_chunks = (2 * h->sm_count + n_osc - 1) / n_osc;
     want_chunks = std::max(1, std::min(want_chunks, std::max(1, T.n_etrue / 4)));
     int cb = (T.n_etrue + want_chunks - 1) / want_chunks;
     cb = std::max(1, std::min(cb, cb_max));
     const int n_chunks = (T.n_etrue + cb - 1) / cb;
-    size_t sm = osc_smem_bytes(T.n_layers, cb);
+    size_t sm = osc_smem_bytes(T.n_ltbl, cb);
     const bool seg = sm + h->seg_bytes <= std::min<size_t>(h->osc_smem_limit, 110 * 1024);
     if (seg) sm += h->seg_bytes;
     OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0, n_var};

@@ -59,6 +59,8 @@ struct DevDetector {
 
 struct DevTables {
     int n_etrue, n_e, n_cosz, n_sub, n_paths, n_layers, n_solar, n_seg, n_det, n_params;
+    int n_ltbl;                // layers some path actually crosses (1 + the largest layer id in use): the eigen table
+                               // holds only these (the default binning never reaches PREM's innermost layer)
     int fast, earth_unc;
     const double* e_calc;      // [n_e]
     const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path

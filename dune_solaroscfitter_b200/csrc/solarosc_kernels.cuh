@@ -209,7 +209,7 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
                                           int vcol = -1, double vdelta = 0.0) {
     // (vcol, vdelta): parameter column shifted by vdelta -- the finite-difference variants of the gradient path
     const int ne = 2 * cb;   // fine energies handled here
-    const int nl = T.n_layers;
+    const int nl = T.n_ltbl;
     // mixing parameters (reference propagation_osc.jl:30-36: theta = asin(sqrt(clamp(sin2, 0, 1))))
     const double s12sq = fmin(fmax(p[0] + (vcol == 0 ? vdelta : 0.0), 0.0), 1.0);
     const double s13sq = fmin(fmax(p[1] + (vcol == 1 ? vdelta : 0.0), 0.0), 1.0);
@@ -367,8 +367,8 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     const int cb = min(L.cb, T.n_etrue - i0);            // coarse bins handled here
     const int nrow = 1 + T.n_cosz;
     double* tbl = smem;                                  // [nl][2 parity][cbs] entries of kEntry doubles
-    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * L.cb;   // [2 proc][2 what][2 parity][cbs]
-    const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_layers, L.cb), L.seg_smem != 0);
+    double* msw = smem + (size_t)kEntry * T.n_ltbl * 2 * L.cb;   // [2 proc][2 what][2 parity][cbs]
+    const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_ltbl, L.cb), L.seg_smem != 0);
     GlobalSink sink{osc_out + (size_t)g * 2 * nrow * T.n_etrue, osc_out + ((size_t)g * 2 + 1) * nrow * T.n_etrue, T.n_etrue};
     double* p1e = p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr;
     if (L.seg_smem) osc_stage<true>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink, vcol, vdelta);
@@ -830,8 +830,8 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     SOLAROSC_PH(0);
     const int cbs = L.osc_cb;
     double* tbl = smem;
-    double* msw = smem + (size_t)kEntry * T.n_layers * 2 * cbs;
-    double* p8s = smem + osc_smem_doubles(T.n_layers, cbs);   // [nrow][ldp] per process, no padding rows (llh_smem_bytes)
+    double* msw = smem + (size_t)kEntry * T.n_ltbl * 2 * cbs;
+    double* p8s = smem + osc_smem_doubles(T.n_ltbl, cbs);   // [nrow][ldp] per process, no padding rows (llh_smem_bytes)
     double* phs = p8s + (size_t)nrow * ldp;
     double* scr = phs + (size_t)nrow * ldp;
     const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), true);   // the host only launches this kernel when they fit
