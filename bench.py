@@ -261,7 +261,7 @@ def main():
     out_np = h_lnl.numpy()
 
     def step_e2e():
-        out_np[:] = eng.eval_llh(h_np)         # H2D of the step's inputs + kernels + D2H of lnL, all inside
+        eng.eval_llh(h_np, out=out_np)         # H2D of the step's inputs + kernels + D2H of lnL, all inside
         if world > 1:
             dist.barrier()
 

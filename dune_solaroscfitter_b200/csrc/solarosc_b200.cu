@@ -75,8 +75,8 @@ struct solarosc_handle {
     double* d_osc = nullptr;
     double* d_lnl2[2]{};
     uint32_t* d_flags2[2]{};
-    uint32_t* h_flags = nullptr; // pinned, grown on demand (n_points)
-    size_t h_flags_n = 0;
+    double* h_lnl2[2]{};         // pinned staging of the results of one chunk, double-buffered
+    uint32_t* h_flags2[2]{};
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
     double* d_gradws = nullptr;  // gradient path: probabilities of each point and its shifted copies, then the gradients
     size_t gradws_bytes = 0;
@@ -435,6 +435,8 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         h->d_params2[i] = h->dalloc<double>((size_t)h->chunk * h->P);
         h->d_lnl2[i] = h->dalloc<double>(h->chunk);
         h->d_flags2[i] = h->dalloc<uint32_t>(h->chunk);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_lnl2[i]), (size_t)h->chunk * sizeof(double)));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags2[i]), (size_t)h->chunk * sizeof(uint32_t)));
     }
     h->d_params = h->d_params2[0];
     h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
@@ -598,8 +600,8 @@ int guarded(solarosc_handle* h, F&& body) {
 
 // Host-buffer likelihood evaluation.  Three streams form a pipeline over chunks: H2D of chunk c+1
 // (straight from the caller's buffer: asynchronous when it is pinned, staged by the driver when
-// pageable) overlaps the two kernels of chunk c and the D2H of chunk c-1; the host thread only
-// enqueues and synchronises once at the end.
+// pageable) overlaps the two kernels of chunk c and the D2H of chunk c-1 into pinned staging; the host thread
+// enqueues two chunks ahead and meanwhile hands the finished chunks to the caller's arrays.
 int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t group, double* out, uint32_t* flags) {
     REQUIRE(params && out, "params and out_lnl must not be NULL");
     REQUIRE(group >= 1 && n % group == 0, "n_points must be a multiple of group");
@@ -608,18 +610,28 @@ int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t gro
     h->launches = 0;
     h->tev_used = 0;
     h->tev_stream = h->stream;
-    if (n > h->h_flags_n) {
-        if (h->h_flags) CK(cudaFreeHost(h->h_flags));
-        h->h_flags = nullptr; h->h_flags_n = 0;
-        CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), n * sizeof(uint32_t)));
-        h->h_flags_n = n;
-    }
+    // results come back through two pinned staging slots and are handed to the caller's (possibly pageable) arrays by
+    // the host thread two chunks behind the GPU: every copy on the streams stays asynchronous
     const size_t step = ((size_t)h->chunk / group) * group;
+    bool neg = false;
+    auto drain = [&](size_t c) {
+        const size_t b0 = c * step;
+        const size_t nb = std::min(step, n - b0);
+        const int slot = (int)(c & 1);
+        std::memcpy(out + b0, h->h_lnl2[slot], nb * sizeof(double));
+        const uint32_t* f = h->h_flags2[slot];
+        for (size_t i = 0; i < nb; ++i) neg |= (f[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+        if (flags) std::memcpy(flags + b0, f, nb * sizeof(uint32_t));
+    };
     size_t c = 0;
     for (size_t b0 = 0; b0 < n; b0 += step, ++c) {
         const int nb = (int)std::min(step, n - b0);
         const int slot = (int)(c & 1);
-        if (c >= 2) CK(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 have read this slot
+        if (c >= 2) {
+            CK(cudaEventSynchronize(h->ev_out[slot]));                           // chunk c-2 has landed in this staging slot
+            drain(c - 2);
+            CK(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));               // kernels of chunk c-2 have read this parameter slot
+        }
         CK(cudaMemcpyAsync(h->d_params2[slot], params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
         CK(cudaEventRecord(h->ev_in[slot], h->s_in));
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
@@ -632,15 +644,13 @@ int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t gro
         if (h->timing) CK(cudaEventRecord(h->next_tev(), h->stream));
         CK(cudaEventRecord(h->ev_done[slot], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
-        CK(cudaMemcpyAsync(out + b0, h->d_lnl2[slot], nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
-        CK(cudaMemcpyAsync(h->h_flags + b0, h->d_flags2[slot], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaMemcpyAsync(h->h_lnl2[slot], h->d_lnl2[slot], nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaMemcpyAsync(h->h_flags2[slot], h->d_flags2[slot], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_out));
         CK(cudaEventRecord(h->ev_out[slot], h->s_out));
     }
     CK(cudaStreamSynchronize(h->s_out));
     CK(cudaStreamSynchronize(h->stream));
-    bool neg = false;
-    for (size_t i = 0; i < n; ++i) neg |= (h->h_flags[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
-    if (flags) std::memcpy(flags, h->h_flags, n * sizeof(uint32_t));
+    for (size_t k = c >= 2 ? c - 2 : 0; k < c; ++k) drain(k);
     if (neg) {
         h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
         return SOLAROSC_ERR_NEGATIVE_RATE;
@@ -780,7 +790,10 @@ void solarosc_destroy(solarosc_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_gradws) cudaFree(h->d_gradws);
-    if (h->h_flags) cudaFreeHost(h->h_flags);
+    for (int i = 0; i < 2; ++i) {
+        if (h->h_lnl2[i]) cudaFreeHost(h->h_lnl2[i]);
+        if (h->h_flags2[i]) cudaFreeHost(h->h_flags2[i]);
+    }
     for (int i = 0; i < 2; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);

@@ -100,11 +100,15 @@ class SolarOscEngine:
         a = [np.ascontiguousarray(data[k], dtype=np.float64) for k in ("ES_day", "ES_night", "CC_day", "CC_night")]
         self._check(self._L.solarosc_set_data(self._h, det, *[_dp(x) for x in a]))
 
-    def eval_llh(self, params, group: int = 1, return_flags: bool = False, raise_on_negative: bool = False):
+    def eval_llh(self, params, group: int = 1, return_flags: bool = False, raise_on_negative: bool = False,
+                 out: Optional[np.ndarray] = None):
         p = self._params(params)
-        out = np.empty(len(p))
-        fl = np.zeros(len(p), dtype=np.uint32)
-        fp = fl.ctypes.data_as(C.POINTER(C.c_uint32))
+        if out is None:
+            out = np.empty(len(p))
+        elif out.shape != (len(p),) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array with one entry per point")
+        fl = np.zeros(len(p), dtype=np.uint32) if return_flags else None      # the library takes NULL for "no flags"
+        fp = fl.ctypes.data_as(C.POINTER(C.c_uint32)) if return_flags else None
         if group == 1:
             st = self._L.solarosc_eval_llh(self._h, _dp(p), len(p), _dp(out), fp)
         else:
