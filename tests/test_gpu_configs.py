@@ -182,3 +182,42 @@ def test_c5_device_block_sums_match_the_replay_loop(engine, tables, asimov, draw
     # block sums add: two calls on the halves equal one call on the whole
     a, b = engine.eval_derived(p[:500], w[:500], lref), engine.eval_derived(p[500:], w[500:], lref)
     assert close(a["mom_CC"] + b["mom_CC"], got["mom_CC"], 1e-12) and close(a["scalars"] + b["scalars"], got["scalars"], 1e-12)
+
+
+# ---- C2: the full 512 x 512 x 27 LLH scan through size-independent properties --------------------------------------------
+def test_c2_full_scan_properties(engine, tables, asimov):
+    """BASELINE.json configs[1] at full size (7.08 M points, llhScan.jl:35-37,48-108).  The oracle cannot visit every
+    point in test time, so: (1) an evenly spaced sample against the C oracle at the stated tolerance; (2) the scan's
+    structure -- the centre points of a cell row reproduce a direct evaluation of those points in a small batch,
+    bit for bit, whatever their position in the 7 M-point call; (3) a shuffled copy of a slice of the scan returns
+    the same values, permuted; (4) the grouped evaluation (27 points of a cell share the oscillation stage) agrees
+    with the ungrouped one to summation order; (5) the minimum of -2lnL over the scan sits in the cell nearest the truth."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import scan_params
+    from oracle import oracle_c
+    grid = 512
+    p, n_cell = scan_params(tables, grid, float(tables["truth"][1]))
+    assert p.shape == (grid * grid * 27, 19) and n_cell == 27
+    lnl, fl = engine.eval_llh(p, return_flags=True)
+    assert np.all(np.isfinite(lnl)) and not np.any(fl)
+    # (1) sample against the oracle
+    idx = np.arange(0, len(p), len(p) // 300)[:300]
+    ref, _ = oracle_c.COracle(tables, asimov).eval_llh(np.ascontiguousarray(p[idx]))
+    assert np.max(np.abs(2 * lnl[idx] - 2 * ref)) < 1e-6
+    # (2) position independence, bit for bit
+    row = (np.arange(grid) * grid + 200) * 27 + 26            # centre point (no nuisance shift) of the cells of column 200
+    assert np.array_equal(engine.eval_llh(np.ascontiguousarray(p[row])), lnl[row])
+    # (3) permutation
+    rng = np.random.default_rng(5)
+    sl = slice(3_000_000, 3_200_000)
+    perm = rng.permutation(200_000)
+    assert np.array_equal(engine.eval_llh(np.ascontiguousarray(p[sl][perm])), lnl[sl][perm])
+    # (4) grouped evaluation
+    g = engine.eval_llh(p, group=27)
+    assert np.max(np.abs(g - lnl)) < 1e-9
+    # (5) the scan's minimum is at the truth (Asimov data): sin2_th12 = 0.307, dm2_21 = 6e-5
+    centre = lnl.reshape(grid, grid, 27)[:, :, 26]
+    i, j = np.unravel_index(np.argmax(centre), centre.shape)
+    v12, vdm = np.linspace(0.2, 0.4, grid), np.linspace(4e-5, 1.5e-4, grid)
+    assert abs(v12[i] - 0.307) <= (v12[1] - v12[0]) and abs(vdm[j] - 6e-5) <= (vdm[1] - vdm[0])
