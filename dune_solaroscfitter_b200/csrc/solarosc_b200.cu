@@ -1055,16 +1055,22 @@ int solarosc_poisson_llh(solarosc_handle* h, const double* expected, const doubl
         if (n_vec == 0) return (int)SOLAROSC_OK;
         REQUIRE(expected && measured && out, "NULL pointer");
         const size_t tot = n_vec * len;
-        h->ensure_scratch((2 * tot + n_vec) * sizeof(double) + n_vec * sizeof(uint32_t));
+        // enough CTAs for every SM: long vectors are cut into segments (at least 2048 terms each)
+        const int n_split = (int)std::max<size_t>(1, std::min<size_t>(((size_t)4 * h->sm_count + n_vec - 1) / n_vec, (len + 2047) / 2048));
+        const size_t n_part = n_vec * n_split;
+        h->ensure_scratch((2 * tot + n_vec + n_part) * sizeof(double) + (n_vec + n_part) * sizeof(uint32_t));
         double* de = h->d_scratch;
         double* dm = de + tot;
         double* dout = dm + tot;
-        uint32_t* df = reinterpret_cast<uint32_t*>(dout + n_vec);
+        double* dpart = dout + n_vec;
+        uint32_t* df = reinterpret_cast<uint32_t*>(dpart + n_part);
+        uint32_t* dpf = df + n_vec;
         CK(cudaMemcpyAsync(de, expected, tot * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(dm, measured, tot * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        poisson_kernel<<<(unsigned)n_vec, 256, 0, h->stream>>>(de, dm, len, dout, df);
+        poisson_kernel<<<(unsigned)n_part, 256, 0, h->stream>>>(de, dm, len, n_split, dpart, dpf);
+        poisson_finish_kernel<<<(unsigned)((n_vec + 127) / 128), 128, 0, h->stream>>>(dpart, dpf, n_vec, n_split, dout, df);
         CK(cudaGetLastError());
-        h->launches = 1;
+        h->launches = 2;
         CK(cudaMemcpyAsync(out, dout, n_vec * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         std::vector<uint32_t> fl(n_vec);
         CK(cudaMemcpyAsync(fl.data(), df, n_vec * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));

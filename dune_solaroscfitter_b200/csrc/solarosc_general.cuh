@@ -23,7 +23,7 @@
 
 namespace solarosc {
 
-constexpr int kMCg = 4;   // row tiles in flight (two accumulator sets per tile)
+constexpr int kMCg = 2;   // row tiles in flight (two accumulator sets per tile)
 
 struct GenLaunch {
     // output strides of the angular ES arrays (cos bin, reco bin, zenith bin) for day and night
@@ -146,8 +146,13 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
         }
         __syncthreads();
         double part = 0.0;
-        for (int col = warp; col < nte + ntc; col += kWarps) {
-            const bool is_es = col < nte;
+        // work items: (column block, group of kMCg row tiles), the ES blocks first (with the angular reconstruction they
+        // carry n_cos times the Poisson terms), dealt round-robin over the warps
+        const int npass = (mt + kMCg - 1) / kMCg;
+        for (int task = warp; task < (nte + ntc) * npass; task += kWarps) {
+            const bool is_es = task < nte * npass;
+            const int tt = is_es ? task : task - nte * npass, nc_ = is_es ? nte : ntc;
+            const int pass = tt / nc_, col = (is_es ? 0 : nte) + (tt - pass * nc_);
             if (is_es ? !es_on : !cc_on) continue;
             const int n0 = 8 * (is_es ? col : col - nte);
             const int ldb = 8 * (is_es ? nte : ntc);
@@ -163,7 +168,8 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
             const double i10 = v0 ? (is_es ? cst1_es : cst_cc)[j0] : 0.0, i11 = v1 ? (is_es ? cst1_es : cst_cc)[j0 + 1] : 0.0;
             const double i20 = (v0 && is_es) ? cst2_es[j0] : 0.0, i21 = (v1 && is_es) ? cst2_es[j0 + 1] : 0.0;
             const size_t bstep = (size_t)4 * ldb;
-            for (int m0 = 0; m0 < mt; m0 += kMCg) {
+            {
+                const int m0 = pass * kMCg;
                 double a1[kMCg][2], a2[kMCg][2];
                 uint32_t pa[kMCg];
 #pragma unroll
@@ -196,18 +202,25 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                     }
                 }
                 // ---- epilogue ----------------------------------------------------------------------------
+                double r1[kMCg][2], r2[kMCg][2];
+                bool vr[kMCg];
 #pragma unroll
                 for (int c = 0; c < kMCg; ++c) {
                     const int row = 8 * (m0 + c) + fg;
-                    if (m0 + c >= mt || row >= nrow) continue;
-                    const double w = (row == 0) ? 1.0 : T.wz[row - 1];
+                    vr[c] = m0 + c < mt && row < nrow;
+                    const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int jx = j0 + hh;
-                        if (jx >= nR) continue;
-                        const double r1 = w * a1[c][hh], r2 = w * a2[c][hh];
-                        if (!(is_es && D.ang)) {
-                            const double r = r1 + r2;
+                    for (int hh = 0; hh < 2; ++hh) { r1[c][hh] = w * a1[c][hh]; r2[c][hh] = w * a2[c][hh]; }
+                }
+                if (!(is_es && D.ang)) {
+#pragma unroll
+                    for (int c = 0; c < kMCg; ++c) {
+                        const int row = 8 * (m0 + c) + fg;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int jx = j0 + hh;
+                            if (!vr[c] || jx >= nR) continue;
+                            const double r = r1[c][hh] + r2[c][hh];
                             if (MODE == kModeLlh) {
                                 if (jx >= idx0) {
                                     const double2 ol = __ldg((is_es ? D.ol_es : D.ol_cc) + row * nR + jx);
@@ -220,22 +233,48 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                                 if (row == 0) { if (day) day[b * nR + jx] = r; }
                                 else if (night) night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = r;
                             }
+                        }
+                    }
+                } else {
+                    // every cos-scatter bin of this lane's (row, reco bin) elements: llh_ES_angle sums them all.  The cos
+                    // bin is the outer loop so that the 2 kMCg Poisson terms of one bin are independent chains.
+                    const bool in0 = v0 && j0 >= idx0, in1 = v1 && j0 + 1 >= idx0;
+                    const double* am0 = D.angm + (size_t)min(j0, nR - 1) * ncos;
+                    const double* am1 = D.angm + (size_t)min(j0 + 1, nR - 1) * ncos;
+                    const double* bm0 = D.bgang + (size_t)min(j0, nR - 1) * ncos;
+                    const double* bm1 = D.bgang + (size_t)min(j0 + 1, nR - 1) * ncos;
+                    for (int cs = 0; cs < ncos; ++cs) {
+                        const double ga0 = __ldg(am0 + cs), ga1 = __ldg(am1 + cs), gb0 = __ldg(bm0 + cs), gb1 = __ldg(bm1 + cs);
+                        if (MODE == kModeLlh) {
+                            double2 o0[kMCg], o1[kMCg];
+#pragma unroll
+                            for (int c = 0; c < kMCg; ++c) {
+                                const int row = min(8 * (m0 + c) + fg, nrow - 1);
+                                o0[c] = (vr[c] && in0) ? __ldg(D.ol_es_ang + ((size_t)row * nR + j0) * ncos + cs) : make_double2(0.0, 0.0);
+                                o1[c] = (vr[c] && in1) ? __ldg(D.ol_es_ang + ((size_t)row * nR + j0 + 1) * ncos + cs) : make_double2(0.0, 0.0);
+                            }
+#pragma unroll
+                            for (int c = 0; c < kMCg; ++c) {
+                                const double e0 = fma(ga0, r1[c][0], gb0 * r2[c][0]), e1 = fma(ga1, r1[c][1], gb1 * r2[c][1]);
+                                const double t0 = poisson_term((vr[c] && in0) ? e0 : 1.0, o0[c].x, o0[c].y, fl);
+                                const double t1 = poisson_term((vr[c] && in1) ? e1 : 1.0, o1[c].x, o1[c].y, fl);
+                                part += ((vr[c] && in0) ? t0 : 0.0) + ((vr[c] && in1) ? t1 : 0.0);
+                            }
                         } else {
-                            // every cos-scatter bin of this (row, reco bin): llh_ES_angle sums them all
-                            const double* am = D.angm + (size_t)jx * ncos;
-                            const double* bm = D.bgang + (size_t)jx * ncos;
-                            const double2* ol = D.ol_es_ang + ((size_t)row * nR + jx) * ncos;
-                            for (int cs = 0; cs < ncos; ++cs) {
-                                const double r = fma(__ldg(am + cs), r1, __ldg(bm + cs) * r2);
-                                if (MODE == kModeLlh) {
-                                    if (jx >= idx0) {
-                                        const double2 o2 = __ldg(ol + cs);
-                                        part += poisson_term(r, o2.x, o2.y, fl);
+#pragma unroll
+                            for (int c = 0; c < kMCg; ++c) {
+                                const int row = 8 * (m0 + c) + fg;
+                                if (!vr[c]) continue;
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int jx = j0 + hh;
+                                    if (jx >= nR) continue;
+                                    const double r = fma(hh ? ga1 : ga0, r1[c][hh], (hh ? gb1 : gb0) * r2[c][hh]);
+                                    if (row == 0) {
+                                        if (O.es_day) O.es_day[b * (size_t)ncos * nR + cs * GL.d_c + jx * GL.d_j] = r;
+                                    } else if (O.es_night) {
+                                        O.es_night[b * (size_t)ncos * nR * nZ + cs * GL.n_c + jx * GL.n_j + (row - 1) * GL.n_z] = r;
                                     }
-                                } else if (row == 0) {
-                                    if (O.es_day) O.es_day[b * (size_t)ncos * nR + cs * GL.d_c + jx * GL.d_j] = r;
-                                } else if (O.es_night) {
-                                    O.es_night[b * (size_t)ncos * nR * nZ + cs * GL.n_c + jx * GL.n_j + (row - 1) * GL.n_z] = r;
                                 }
                             }
                         }

@@ -973,15 +973,19 @@ __global__ void __launch_bounds__(256) derived_finish_kernel(int n_slices, int n
 //  tests/benchmark_likelihoods.jl:10-19)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-poisson_kernel(const double* __restrict__ e, const double* __restrict__ m, size_t len, double* __restrict__ out,
-               uint32_t* __restrict__ flags) {
+poisson_kernel(const double* __restrict__ e, const double* __restrict__ m, size_t len, int n_split, double* __restrict__ part,
+               uint32_t* __restrict__ part_flags) {
+    // CTA (v, s) sums segment s of vector v (a handful of long vectors would otherwise leave most SMs idle);
+    // poisson_finish_kernel adds the segments in order
     __shared__ double red[8];
     __shared__ uint32_t redf[8];
-    const double* ev = e + (size_t)blockIdx.x * len;
-    const double* mv = m + (size_t)blockIdx.x * len;
+    const size_t v = blockIdx.x / n_split, sgm = blockIdx.x - v * n_split;
+    const size_t per = (len + n_split - 1) / n_split, i0 = sgm * per, i1 = i0 + per < len ? i0 + per : len;
+    const double* ev = e + v * len;
+    const double* mv = m + v * len;
     double acc = 0.0;
     uint32_t fl = 0;
-    for (size_t i = threadIdx.x; i < len; i += blockDim.x) {
+    for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const double mm = mv[i];
         acc += poisson_term(ev[i], mm, mm > 0.0 ? log(mm) : 0.0, fl);
     }
@@ -990,12 +994,23 @@ poisson_kernel(const double* __restrict__ e, const double* __restrict__ m, size_
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redf[threadIdx.x >> 5] = fl; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0.0;
+        double t = 0.0;
         uint32_t f = 0;
-        for (int w = 0; w < 8; ++w) { s += red[w]; f |= redf[w]; }
-        out[blockIdx.x] = (f & SOLAROSC_FLAG_NEG_ERROR) ? NAN : -s;
-        if (flags) flags[blockIdx.x] = f;
+        for (int w = 0; w < 8; ++w) { t += red[w]; f |= redf[w]; }
+        part[blockIdx.x] = t;
+        part_flags[blockIdx.x] = f;
     }
+}
+
+__global__ void poisson_finish_kernel(const double* __restrict__ part, const uint32_t* __restrict__ part_flags, size_t n_vec,
+                                      int n_split, double* __restrict__ out, uint32_t* __restrict__ flags) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vec) return;
+    double t = 0.0;
+    uint32_t f = 0;
+    for (int k = 0; k < n_split; ++k) { t += part[v * n_split + k]; f |= part_flags[v * n_split + k]; }
+    out[v] = (f & SOLAROSC_FLAG_NEG_ERROR) ? NAN : -t;
+    if (flags) flags[v] = f;
 }
 
 // ------------------------------------------------------------------------------------------
