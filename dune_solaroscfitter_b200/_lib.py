@@ -19,7 +19,7 @@ _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
-    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_grad", "solarosc_eval_rates",
+    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_multi", "solarosc_eval_llh_grad", "solarosc_eval_rates",
     "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_derived", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
     "solarosc_batcher_create", "solarosc_batcher_create_with", "solarosc_batcher_eval", "solarosc_batcher_leave",
@@ -74,6 +74,7 @@ def load():
     L.solarosc_eval_rates.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp, dp, dp]
     L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
     L.solarosc_eval_asymmetry.argtypes = [H, C.c_int, dp, sz, dp, dp]
+    L.solarosc_eval_llh_multi.argtypes = [C.POINTER(H), sz, dp, sz, sz, dp, C.POINTER(C.c_uint32)]
     L.solarosc_eval_derived.argtypes = [H, C.c_int, dp, sz] + [dp] * 11
     ip, u8 = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     L.solarosc_setup_bin_index.argtypes = [dp, sz, dp, sz, ip]

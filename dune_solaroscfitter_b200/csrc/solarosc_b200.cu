@@ -12,6 +12,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "solarosc_grad.cuh"
@@ -828,6 +829,33 @@ int solarosc_eval_llh(solarosc_handle* h, const double* params, size_t n, double
 int solarosc_eval_llh_grouped(solarosc_handle* h, const double* params, size_t n, size_t group, double* out,
                               uint32_t* flags) {
     return guarded(h, [&]() { return n == 0 ? (int)SOLAROSC_OK : eval_llh_host(h, params, n, group, out, flags); });
+}
+
+// One process driving several GPUs: the rows are dealt to the handles in contiguous slices (whole groups), each slice
+// is evaluated by its own host thread on its own device, and every slice's lnL lands directly in the caller's array.
+int solarosc_eval_llh_multi(solarosc_handle* const* hs, size_t n_handles, const double* params, size_t n, size_t group,
+                            double* out, uint32_t* flags) {
+    if (!hs || n_handles == 0) return SOLAROSC_ERR_ARG;
+    for (size_t k = 0; k < n_handles; ++k)
+        if (!hs[k] || hs[k]->P != hs[0]->P) return SOLAROSC_ERR_ARG;
+    if (n == 0) return SOLAROSC_OK;
+    if (!params || !out || group == 0 || n % group) return SOLAROSC_ERR_ARG;
+    const size_t n_groups = n / group, base = n_groups / n_handles, extra = n_groups % n_handles;
+    std::vector<int> status(n_handles, SOLAROSC_OK);
+    std::vector<std::thread> workers;
+    const size_t P = (size_t)hs[0]->P;
+    for (size_t k = 0; k < n_handles; ++k) {
+        const size_t lo = (k * base + std::min(k, extra)) * group, hi = lo + (base + (k < extra ? 1 : 0)) * group;
+        if (hi == lo) continue;
+        workers.emplace_back([=, &status]() {
+            status[k] = guarded(hs[k], [&]() { return eval_llh_host(hs[k], params + lo * P, hi - lo, group, out + lo, flags ? flags + lo : nullptr); });
+        });
+    }
+    for (auto& w : workers) w.join();
+    int worst = SOLAROSC_OK;
+    for (int st : status)
+        if (st != SOLAROSC_OK && (worst == SOLAROSC_OK || worst == SOLAROSC_ERR_NEGATIVE_RATE)) worst = st;
+    return worst;
 }
 
 int solarosc_eval_llh_grad(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad,

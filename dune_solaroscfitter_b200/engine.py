@@ -237,6 +237,21 @@ class SolarOscEngine:
         return dict(ms_osc=a.value, ms_rates=b.value, launches=n, fused=bool(self._L.solarosc_last_fused(self._h)))
 
 
+def eval_llh_multi(engines: Sequence["SolarOscEngine"], params, group: int = 1, return_flags: bool = False):
+    """One batch dealt over several engines (one per GPU, same tables) from this process: contiguous slices of whole
+    groups, evaluated concurrently, lnL of every slice written straight into one result array
+    (solarosc_eval_llh_multi)."""
+    e0 = engines[0]
+    p = e0._params(params)
+    out = np.empty(len(p))
+    fl = np.zeros(len(p), dtype=np.uint32)
+    hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    st = e0._L.solarosc_eval_llh_multi(hs, len(engines), _dp(p), len(p), group, _dp(out), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if st != abi.ERR_NEGATIVE_RATE:
+        e0._check(st)
+    return (out, fl) if return_flags else out
+
+
 class Batcher:
     """N threads each call ``eval(slot, params)`` with ONE point; one batched launch serves them all."""
 

@@ -24,6 +24,7 @@
  *   solarosc_eval_llh_grouped  the same for llhScan.jl:84-116, where the n_sys x 3 points of a
  *                          grid cell share one oscillation stage (precomputed_osc,
  *                          propagation_main.jl:60-66)
+ *   solarosc_eval_llh_multi  the same batch dealt over the GPUs of one box from a single host process
  *   solarosc_eval_llh_grad the value + gradient BAT's HMC asks of that log-density (mcmc.jl:102-103, where the
  *                          reference differentiates total_llh with ForwardDiff)
  *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
@@ -192,6 +193,14 @@ int solarosc_eval_llh(solarosc_handle *h, const double *params, size_t n_points,
  * point g*group.  n_points must be a multiple of group. */
 int solarosc_eval_llh_grouped(solarosc_handle *h, const double *params, size_t n_points, size_t group,
                               double *out_lnl, uint32_t *out_flags);
+
+/* Several GPUs from one process: hs[k] are handles created from the same tables on different devices
+ * (solarosc_config.device).  The n_points rows are dealt to the handles in contiguous slices of whole groups, every
+ * slice is evaluated concurrently by its own host thread, and each slice's lnL is copied straight into out_lnl --
+ * the gather of the per-point vector that a multi-process run does with NCCL (bench.py, sharding.py) happens here
+ * through the host array the caller wants the results in anyway.  group = 1 for independent points. */
+int solarosc_eval_llh_multi(solarosc_handle *const *hs, size_t n_handles, const double *params, size_t n_points,
+                            size_t group, double *out_lnl, uint32_t *out_flags);
 
 /* lnL and d lnL / d params for every point: out_grad[b*P + k] = d lnL_b / d params[b][k].  Fluxes, cross-section
  * and background norms are differentiated analytically (reverse mode through the fold); the oscillation columns

@@ -314,6 +314,24 @@ function compute_shared_osc_probs(params, solarModel; nz::Int, nT::Int)
 end
 
 """
+    total_llh_batch_multi(handles, params; group=1)
+
+The same batch dealt over several handles -- one per GPU of the box, each created by `init_engine(...; device=k)` and
+collected in `handles::Vector{Ptr{Cvoid}}` -- from this one Julia process: every GPU evaluates its own contiguous
+slice and the slices' lnL land in one vector (`solarosc_eval_llh_multi`; no NCCL, no extra processes).
+"""
+function total_llh_batch_multi(handles::Vector{Ptr{Cvoid}}, params; group::Int=1)
+    M = pack_many(params); B = size(M, 2)
+    out = Vector{Float64}(undef, B); flags = Vector{UInt32}(undef, B)
+    GC.@preserve handles M out flags begin
+        check(@ccall libb200.solarosc_eval_llh_multi(pointer(handles)::Ptr{Ptr{Cvoid}}, Csize_t(length(handles))::Csize_t,
+            pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t, Csize_t(group)::Csize_t, pointer(out)::Ptr{Cdouble},
+            pointer(flags)::Ptr{UInt32})::Cint)
+    end
+    return out
+end
+
+"""
     derived_block_sums(params, weights, lref; det, nz, nes, ncc)
 
 The replay loop of derive_variables_from_chain.jl:260-444 over a block of thinned-in chain samples, reduced on the

@@ -96,3 +96,26 @@ def test_empty_and_single_point_batches(engine, tables):
     assert one.shape == (1,) and abs(one[0]) < 1e-6             # Asimov data at the truth: zero deviance
     a_es, a_cc = engine.eval_asymmetry(p)
     assert a_es.shape == (1,) and np.isfinite(a_cc[0])
+
+
+def test_one_process_several_handles(tables, asimov, draw):
+    """solarosc_eval_llh_multi: the batch dealt over handles (one per GPU where the box has several; two handles on the
+    one GPU otherwise), whole groups per slice, identical bits to a single handle."""
+    import torch
+    from dune_solaroscfitter_b200.engine import SolarOscEngine, eval_llh_multi
+    n_dev = max(1, torch.cuda.device_count())
+    devs = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    p = draw(tables, 27 * 701, seed=21)                       # 701 groups of 27: the slices cannot be equal
+    p[27 * 50, 9] = 2.5                                       # one out-of-bounds earth norm
+    engines = [SolarOscEngine(tables, data=asimov, device=d) for d in devs]
+    try:
+        one, f1 = engines[0].eval_llh(p, return_flags=True)
+        many, fm = eval_llh_multi(engines, p, group=1, return_flags=True)
+        assert np.array_equal(one, many) and np.array_equal(f1, fm) and many[27 * 50] == -np.inf
+        g1 = engines[0].eval_llh(p, group=27)
+        gm = eval_llh_multi(engines, p, group=27)
+        assert np.array_equal(g1, gm)
+        assert eval_llh_multi(engines, p[:0]).shape == (0,)
+    finally:
+        for e in engines:
+            e.close()
