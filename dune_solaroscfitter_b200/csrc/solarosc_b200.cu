@@ -248,6 +248,13 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
             se[zr * T.n_sub + sub] = make_int2(t->seg_start[pth], t->seg_start[pth + 1]);
         }
     T.path_se = h->upload(se.data(), T.n_paths);
+    std::vector<unsigned> row_layers(T.n_cosz, 0u);
+    for (int zr = 0; zr < T.n_cosz; ++zr)
+        for (int sub = 0; sub < T.n_sub; ++sub) {
+            const int pth = order[zr] * T.n_sub + sub;
+            for (int sg = t->seg_start[pth]; sg < t->seg_start[pth + 1]; ++sg) row_layers[zr] |= 1u << app_layer[sg];
+        }
+    T.row_layers = h->upload(row_layers.data(), T.n_cosz);
     T.earth_lookup = h->upload(t->earth_lookup, T.n_layers);
     T.wz = h->upload(t->exposure_weights, T.n_cosz);
     T.avg_ne[0] = t->avg_ne_8b; T.avg_ne[1] = t->avg_ne_hep;
@@ -1191,11 +1198,12 @@ int solarosc_setup_bin_index_device(solarosc_handle* h, const double* edges, siz
     return guarded(h, [&]() {
         REQUIRE(edges && n_edges > 0 && n_edges <= 4096 && (n == 0 || (v && out)), "bad arguments");
         if (n == 0) return (int)SOLAROSC_OK;
-        double *d_e = nullptr, *d_v = nullptr;
-        int32_t* d_o = nullptr;
-        CK(cudaMalloc(reinterpret_cast<void**>(&d_e), n_edges * sizeof(double)));
-        CK(cudaMalloc(reinterpret_cast<void**>(&d_v), n * sizeof(double)));
-        CK(cudaMalloc(reinterpret_cast<void**>(&d_o), n * sizeof(int32_t)));
+        // edges, values and results live in the handle's scratch (grown on demand, freed with the handle)
+        const size_t ne8 = (n_edges + 1) & ~(size_t)1;
+        h->ensure_scratch((ne8 + n) * sizeof(double) + n * sizeof(int32_t));
+        double* d_e = h->d_scratch;
+        double* d_v = d_e + ne8;
+        int32_t* d_o = reinterpret_cast<int32_t*>(d_v + n);
         CK(cudaMemcpyAsync(d_e, edges, n_edges * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(d_v, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
@@ -1203,7 +1211,6 @@ int solarosc_setup_bin_index_device(solarosc_handle* h, const double* edges, siz
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, d_o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        cudaFree(d_e); cudaFree(d_v); cudaFree(d_o);
         return (int)SOLAROSC_OK;
     });
 }

@@ -66,6 +66,7 @@ struct DevTables {
     const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path
     const int2* path_se;       // [n_cosz*n_sub] (first, one-past-last) step of the paths of sorted row zr, sub-path fastest
     const int* row_order;      // [n_cosz] coarse zenith bin of sorted row zr (longest paths first)
+    const unsigned* row_layers;// [n_cosz] bit k set when some path of sorted row zr crosses layer k
     const double* earth_lookup;// [n_layers]
     const double* wz;          // [n_cosz]
     double avg_ne[2];

@@ -220,6 +220,14 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     const double p0 = c12sq * c13sq;                     // P_0 = c12^2 c13^2 (osc.jl:196)
     const double c2 = 1.0 - 2.0 * s12sq;                 // cos(2 theta12)
 
+    // Finite-difference variants of an earth norm (gradient path) only move the rows whose paths cross that layer;
+    // the others are written as 0 in both the + and the - copy (the gradient only uses their difference), and a layer
+    // no path reaches costs nothing at all.
+    const int vlay = (T.earth_unc && vcol >= SOLAROSC_N_FIXED_PARAMS) ? vcol - SOLAROSC_N_FIXED_PARAMS : -1;
+    if (vlay >= T.n_ltbl) {
+        for (int t = threadIdx.x; t < (1 + T.n_cosz) * cb; t += blockDim.x) sink.put(t / cb, i0 + t % cb, 0.0, 0.0);
+        return;
+    }
     SOLAROSC_PH(1);
     // ---- phase 1a: one eigen-system per (fine energy, layer)  (osc.jl:466-470, 370-388) --------
     // two entries per thread and pass: make_entry is branch-free, so the two dependency chains interleave
@@ -298,6 +306,10 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
         const int item = wi * 32 + lane;
         if (item >= n_items) continue;
         const int zr = (int)((item + 0.5) * inv_cb), j = item - zr * cb;   // exact: item < 2^31, cb >= 1
+        if (vlay >= 0 && !((T.row_layers[zr] >> vlay) & 1u)) {
+            sink.put(1 + G.row_order[zr], i0 + j, 0.0, 0.0);
+            continue;
+        }
         double acc8 = 0.0, acch = 0.0;
         const double* t0 = tbl + (size_t)j * kEntry;           // even fine energy of this coarse bin, layer 0
         const double* t1 = t0 + (size_t)cbs * kEntry;          // odd fine energy
