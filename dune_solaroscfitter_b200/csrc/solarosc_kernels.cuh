@@ -211,8 +211,10 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     const int ne = 2 * cb;   // fine energies handled here
     const int nl = T.n_ltbl;
     // mixing parameters (reference propagation_osc.jl:30-36: theta = asin(sqrt(clamp(sin2, 0, 1))))
-    const double s12sq = fmin(fmax(p[0] + (vcol == 0 ? vdelta : 0.0), 0.0), 1.0);
-    const double s13sq = fmin(fmax(p[1] + (vcol == 1 ? vdelta : 0.0), 0.0), 1.0);
+    // clamp(x, 0, 1) that lets a NaN through like Julia's does (fmin / fmax would turn it into 0)
+    auto clamp01 = [](double x) { return x != x ? x : fmin(fmax(x, 0.0), 1.0); };
+    const double s12sq = clamp01(p[0] + (vcol == 0 ? vdelta : 0.0));
+    const double s13sq = clamp01(p[1] + (vcol == 1 ? vdelta : 0.0));
     const double dm21 = p[2] + (vcol == 2 ? vdelta : 0.0);
     const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq;
     const double c13 = sqrt01(c13sq);

@@ -93,6 +93,26 @@ def test_earth_norm_bounds_give_minus_inf(engine, tables):
     assert fl[1] == 1 and fl[2] == 1
 
 
+def test_nan_parameters_give_flagged_nan(engine, tables):
+    """A NaN in any column reaches the result as NaN with the NONFINITE flag (Julia's clamp, asin, exp and the Poisson
+    sum all propagate it); a NaN earth norm fails the bounds check like any other out-of-range value: -Inf."""
+    truth = np.asarray(tables["truth"], dtype=float)
+    p = np.tile(truth, (20, 1))
+    for c in range(19):
+        p[c, c] = np.nan
+    for batch in (p, np.tile(p, (10, 1))):            # small batch: osc_kernel + rates_kernel; large: fused llh_kernel
+        got, fl = engine.eval_llh(batch, return_flags=True)
+        got, fl = got[:20], fl[:20]
+        for c in range(19):
+            if 8 <= c < 14:
+                assert got[c] == -np.inf and fl[c] == 1, c
+            elif c in (15, 16):                        # ES_bg_norm_2, _3 are never read (propagation_bg.jl:56-57)
+                assert abs(got[c]) < 1e-6 and fl[c] == 0, c
+            else:
+                assert np.isnan(got[c]) and fl[c] & 8, c
+        assert abs(got[19]) < 1e-6 and fl[19] == 0
+
+
 def test_grouped_equals_ungrouped(engine, tables, draw):
     g = 9
     p = draw(tables, 4 * g)
