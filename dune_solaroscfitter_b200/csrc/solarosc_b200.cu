@@ -362,6 +362,10 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
                             bm[(size_t)j * D.n_cos + cs] = rb[(size_t)cs * D.n_es + j];
                         }
                     D.angm = h->upload_vec(am); D.bgang = h->upload_vec(bm);
+                    std::vector<double> sa(D.n_es, 0.0), sb(D.n_es, 0.0);
+                    for (int j = 0; j < D.n_es; ++j)
+                        for (int cs = 0; cs < D.n_cos; ++cs) { sa[j] += am[(size_t)j * D.n_cos + cs]; sb[j] += bm[(size_t)j * D.n_cos + cs]; }
+                    D.ang_sa = h->upload_vec(sa); D.ang_sb = h->upload_vec(sb);
                 }
             }
             h->n_cos[d] = D.ang ? D.n_cos : 1;
@@ -459,6 +463,8 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(rates_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(gen_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(gen_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(gen_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+        CK(cudaFuncSetAttribute(gen_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
@@ -536,14 +542,15 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     const RatesLaunch L = rates_launch(h, n, group, det_only);
     const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
     if (h->gen) {
-        if (mode != kModeLlh && mode != kModeRates)
-            throw ArgFail{"per-bin, asymmetry and derived calls serve the exclusive, non-angular analysis only"};
+
         const int d = det_only >= 0 ? det_only : 0;
         const bool cm = h->cfg.col_major != 0;
         const long long nC = h->n_cos[d], nE = h->n_es[d], nZ = T.n_cosz;
         const GenLaunch GL = cm ? GenLaunch{1, nC, 1, nC, nC * nE} : GenLaunch{nE, 1, nE * nZ, nZ, 1};
         if (mode == kModeLlh) gen_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
-        else gen_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        else if (mode == kModeRates) gen_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        else if (mode == kModePerbin) gen_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        else gen_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
         CK(cudaGetLastError());
         ++h->launches;
         return;

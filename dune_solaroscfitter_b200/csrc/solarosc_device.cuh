@@ -54,6 +54,7 @@ struct DevDetector {
     const double *xs8, *xsh;              // CC projected on the ES bins (x f_above), layout of a8
     const double *yp8, *yph, *yc8, *ych;  // mis-identified ES in the CC bins: matrices (layout of b8) and constants
     const double *angm, *bgang;           // [n_es][n_cos]: mask_c ES.angular[c][j], BG.angular[c][j]
+    const double *ang_sa, *ang_sb;        // [n_es]: their sums over the cos-scatter bins
     const double2* ol_es_ang;             // angular ES data (m, log m), [1 + n_cosz][n_es][n_cos]
 };
 

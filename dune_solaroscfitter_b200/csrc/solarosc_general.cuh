@@ -41,6 +41,7 @@ __device__ __forceinline__ void gen_fold_vectors(const DevTables& T, const DevDe
     double* cst1_es = scr + 8 * kt;
     double* cst2_es = cst1_es + 8 * nte;
     double* cst_cc = cst2_es + 8 * nte;
+    double* bgs_cc = cst_cc + 8 * ntc;     // summed CC backgrounds per reco bin (asymmetry mode)
     for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
         double sh = 0.0;
         if (i < nT) {
@@ -76,6 +77,7 @@ __device__ __forceinline__ void gen_fold_vectors(const DevTables& T, const DevDe
                 if (MODE == kModeRates && O.bg_cc) O.bg_cc[b * D.n_cc + jc] = acc;
             }
             cst_cc[jc] = c;
+            if (MODE == kModeAsym) bgs_cc[jc] = acc;
         }
     }
 }
@@ -130,22 +132,24 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
         const int ncos = D.ang ? D.n_cos : 1;
         __syncthreads();
         gen_fold_vectors<MODE>(T, D, p, b, scr, O);
-        if (MODE == kModeRates) {   // disabled channels still produce (zero) arrays (propagation_reco.jl:12-15,119-122)
+        if (MODE == kModeRates || MODE == kModePerbin) {   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
+            const double zv = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
             if (!es_on) {
                 const size_t per_d = (size_t)ncos * D.n_es, per_n = per_d * nZ;
                 for (size_t o = threadIdx.x; o < per_d + per_n; o += blockDim.x) {
-                    if (o < per_d) { if (O.es_day) O.es_day[b * per_d + o] = 0.0; }
-                    else if (O.es_night) O.es_night[b * per_n + (o - per_d)] = 0.0;
+                    if (o < per_d) { if (O.es_day) O.es_day[b * per_d + o] = zv; }
+                    else if (O.es_night) O.es_night[b * per_n + (o - per_d)] = zv;
                 }
             }
             if (!cc_on)
                 for (int o = threadIdx.x; o < nrow * D.n_cc; o += blockDim.x) {
-                    if (o < D.n_cc) { if (O.cc_day) O.cc_day[b * D.n_cc + o] = 0.0; }
-                    else if (O.cc_night) O.cc_night[b * nZ * D.n_cc + (o - D.n_cc)] = 0.0;
+                    if (o < D.n_cc) { if (O.cc_day) O.cc_day[b * D.n_cc + o] = zv; }
+                    else if (O.cc_night) O.cc_night[b * nZ * D.n_cc + (o - D.n_cc)] = zv;
                 }
         }
         __syncthreads();
         double part = 0.0;
+        double d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;   // asymmetry mode: day / night totals above threshold
         // work items: (column block, group of kMCg row tiles), the ES blocks first (with the angular reconstruction they
         // carry n_cos times the Poisson terms), dealt round-robin over the warps
         const int npass = (mt + kMCg - 1) / kMCg;
@@ -226,12 +230,22 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                                     const double2 ol = __ldg((is_es ? D.ol_es : D.ol_cc) + row * nR + jx);
                                     part += poisson_term(r, ol.x, ol.y, fl);
                                 }
+                            } else if (MODE == kModeAsym) {
+                                if (jx >= idx0) {
+                                    if (is_es) { if (row == 0) d_es += r; else n_es += r; }
+                                    else { if (row == 0) d_cc += r; else n_cc += r; }
+                                }
                             } else {
+                                double v = r;
+                                if (MODE == kModePerbin) {   // likelihood_builder.jl:22-51,146-174: bins idx..n-1, the overflow bin excluded
+                                    v = (jx >= idx0 && jx < nR - 1) ? perbin_term(r, __ldg((is_es ? D.ol_es : D.ol_cc) + row * nR + jx).x) : 0.0;
+                                    if (oob) v = -INFINITY;
+                                }
                                 double* day = is_es ? O.es_day : O.cc_day;
                                 double* night = is_es ? O.es_night : O.cc_night;
                                 const long long sr = is_es ? L.s_row_es : L.s_row_cc, sj = is_es ? L.s_j_es : L.s_j_cc;
-                                if (row == 0) { if (day) day[b * nR + jx] = r; }
-                                else if (night) night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = r;
+                                if (row == 0) { if (day) day[b * nR + jx] = v; }
+                                else if (night) night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)jx * sj] = v;
                             }
                         }
                     }
@@ -243,6 +257,18 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                     const double* am1 = D.angm + (size_t)min(j0 + 1, nR - 1) * ncos;
                     const double* bm0 = D.bgang + (size_t)min(j0, nR - 1) * ncos;
                     const double* bm1 = D.bgang + (size_t)min(j0 + 1, nR - 1) * ncos;
+                    if (MODE == kModeAsym) {
+                        // the asymmetry sums every cos-scatter bin (derive_variables_from_chain.jl:239-241): the column sums
+                        // of the angular tables do that once and for all
+#pragma unroll
+                        for (int c = 0; c < kMCg; ++c) {
+                            if (!vr[c]) continue;
+                            double s01 = 0.0;
+                            if (in0) s01 += fma(D.ang_sa[j0], r1[c][0], D.ang_sb[j0] * r2[c][0]);
+                            if (in1) s01 += fma(D.ang_sa[j0 + 1], r1[c][1], D.ang_sb[j0 + 1] * r2[c][1]);
+                            if (8 * (m0 + c) + fg == 0) d_es += s01; else n_es += s01;
+                        }
+                    } else
                     for (int cs = 0; cs < ncos; ++cs) {
                         const double ga0 = __ldg(am0 + cs), ga1 = __ldg(am1 + cs), gb0 = __ldg(bm0 + cs), gb1 = __ldg(bm1 + cs);
                         if (MODE == kModeLlh) {
@@ -269,7 +295,11 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                                 for (int hh = 0; hh < 2; ++hh) {
                                     const int jx = j0 + hh;
                                     if (jx >= nR) continue;
-                                    const double r = fma(hh ? ga1 : ga0, r1[c][hh], (hh ? gb1 : gb0) * r2[c][hh]);
+                                    double r = fma(hh ? ga1 : ga0, r1[c][hh], (hh ? gb1 : gb0) * r2[c][hh]);
+                                    if (MODE == kModePerbin) {   // llh_ES_angle_perbin, likelihood_builder.jl:80-108
+                                        r = (jx >= idx0 && jx < nR - 1) ? perbin_term(r, __ldg(D.ol_es_ang + ((size_t)row * nR + jx) * ncos + cs).x) : 0.0;
+                                        if (oob) r = -INFINITY;
+                                    }
                                     if (row == 0) {
                                         if (O.es_day) O.es_day[b * (size_t)ncos * nR + cs * GL.d_c + jx * GL.d_j] = r;
                                     } else if (O.es_night) {
@@ -279,6 +309,26 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                             }
                         }
                     }
+                }
+            }
+        }
+        if (MODE == kModeAsym) {
+            // derive_variables_from_chain.jl:236-258: half of the background above threshold comes off the day total and half
+            // off the night total; a zero denominator gives 0; the CC asymmetry is not formed in the inclusive analysis
+            for (int ch = 0; ch < 2; ++ch) {
+                const bool is_es = ch == 0;
+                double* out = is_es ? O.asym_es : O.asym_cc;
+                if (is_es ? !es_on : !cc_on) {
+                    if (out && threadIdx.x == 0) out[b] = 0.0;
+                    continue;
+                }
+                const double dtot = block_sum(is_es ? d_es : d_cc, red), ntot = block_sum(is_es ? n_es : n_cc, red);
+                if (threadIdx.x == 0) {
+                    const int nR = is_es ? D.n_es : D.n_cc, idx0 = (is_es ? D.index_es : D.index_cc) - 1;
+                    double bg = 0.0;
+                    for (int j = idx0; j < nR; ++j) bg += is_es ? 2.0 * cst2_es[j] : (cst_cc + 8 * ntc)[j];
+                    const double dd = dtot - 0.5 * bg, nn = ntot - 0.5 * bg, den = dd + nn;
+                    if (out) out[b] = (den == 0.0) ? 0.0 : 2.0 * (dd - nn) / den;
                 }
             }
         }

@@ -260,20 +260,35 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
             msw[(size_t)(proc * 2 + 1) * 2 * cbs + slot] = c13sq * c2m;
         }
     } else {  // osc.jl:139-182: the radius loop is linear in (P_day, cos2theta_m), so both collapse to
-              // production-weighted means; one warp per (process, energy), lanes over radii
+              // production-weighted means of cos(2 theta_m); one warp per fine energy, lanes over radii.  The matter
+              // angle depends on (E, n_e(r)) only, so both processes share it and differ in their weights; the
+              // division by dm21 is taken out of the radius loop (x = cos2theta - n_e(r) kE, one FMA).
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-        for (int t = warp; t < 2 * ne; t += nw) {
-            const int proc = t / ne, el = t - proc * ne;
+        const double s2sq = 1.0 - c2 * c2;
+        const double* __restrict__ sne = T.solar_ne;
+        const double* __restrict__ w8 = T.solar_w[0];
+        const double* __restrict__ wh = T.solar_w[1];
+        for (int el = warp; el < ne; el += nw) {
             const double e = T.e_calc[2 * i0 + el];
-            const double* w = T.solar_w[proc];
-            double acc = 0.0;
-            for (int r = lane; r < T.n_solar; r += 32) acc = fma(w[r], msw_c2m(e, T.solar_ne[r], dm21, c13sq, c2), acc);
-            acc = warp_sum(acc);
+            const double kE = 2.0 * 1.4142135623730951 * kGF * e * c13sq / dm21;
+            double a8 = 0.0, ah = 0.0;
+#pragma unroll 4
+            for (int r = lane; r < T.n_solar; r += 32) {
+                const double x = fma(-sne[r], kE, c2);
+                const double c = x * rsq(fma(x, x, s2sq));
+                a8 = fma(w8[r], c, a8);
+                ah = fma(wh[r], c, ah);
+            }
+            a8 = warp_sum(a8);
+            ah = warp_sum(ah);
             if (lane == 0) {
-                const double c2m = acc / T.solar_wsum[proc];
                 const int slot = (el & 1) * cbs + (el >> 1);
-                msw[(size_t)(proc * 2 + 0) * 2 * cbs + slot] = fma(0.5 * c13sq * c13sq, fma(c2, c2m, 1.0), s13sq * s13sq);
-                msw[(size_t)(proc * 2 + 1) * 2 * cbs + slot] = c13sq * c2m;
+#pragma unroll
+                for (int proc = 0; proc < 2; ++proc) {
+                    const double c2m = (proc ? ah : a8) / T.solar_wsum[proc];
+                    msw[(size_t)(proc * 2 + 0) * 2 * cbs + slot] = fma(0.5 * c13sq * c13sq, fma(c2, c2m, 1.0), s13sq * s13sq);
+                    msw[(size_t)(proc * 2 + 1) * 2 * cbs + slot] = c13sq * c2m;
+                }
             }
         }
     }

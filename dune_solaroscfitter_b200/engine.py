@@ -142,7 +142,8 @@ class SolarOscEngine:
         p = self._params(params)
         n = len(p)
         nes, ncc = self.packed.n_ereco[det]
-        r = dict(ES_day=np.empty((n, nes)), ES_night=self._night(n, nes), CC_day=np.empty((n, ncc)), CC_night=self._night(n, ncc))
+        es_day, es_night = self._es_arrays(n, det)
+        r = dict(ES_day=es_day, ES_night=es_night, CC_day=np.empty((n, ncc)), CC_night=self._night(n, ncc))
         self._check(self._L.solarosc_eval_perbin(self._h, det, _dp(p), n, _dp(r["ES_day"]), _dp(r["ES_night"]),
                                                  _dp(r["CC_day"]), _dp(r["CC_night"])))
         return r

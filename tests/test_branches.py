@@ -98,10 +98,10 @@ def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw)
     with SolarOscEngine(t, data=data) as e:
         a = e.eval_rates(p)
         la = e.eval_llh(p)
-        with pytest.raises(SolarOscError):
-            e.eval_perbin(p)
-        with pytest.raises(SolarOscError):
+        with pytest.raises(SolarOscError):             # gradient and derived-mode sums: exclusive, non-angular analysis only
             e.eval_llh_grad(p)
+        with pytest.raises(SolarOscError):
+            e.eval_derived(p, np.ones(len(p)))
     # the same tables and data as Julia lays them out (column-major: numpy views with reversed shapes)
     tj = dict(t)
     for k in ("resp_es_nue", "resp_es_nuother", "resp_cc", "resp_cc_incl", "resp_es_angular", "resp_bg_angular"):
@@ -114,3 +114,55 @@ def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw)
     assert np.array_equal(b["ES_day"], np.transpose(a["ES_day"], (0, 2, 1)))
     assert np.array_equal(b["ES_night"], np.transpose(a["ES_night"], (0, 3, 2, 1)))
     assert np.array_equal(b["CC_night"], np.transpose(a["CC_night"], (0, 2, 1)))
+
+
+def _perbin_ref(r, m, idx, axis):
+    """per-bin terms on the energy bins idx..n-1 (overflow bin excluded), zeros elsewhere
+    (likelihood_builder.jl:22-51, 80-108, 146-174)."""
+    out = np.zeros_like(r)
+    n = r.shape[axis]
+    sl = [slice(None)] * r.ndim
+    sl[axis] = slice(idx - 1, n - 1)
+    sl = tuple(sl)
+    out[sl] = O.perbin_poisson_log_likelihood(r[sl], m[sl])
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("incl,ang", [(1, 0), (2, 0), (0, 1), (1, 1), (2, 1)])
+def test_perbin_and_asymmetry_of_the_branches(tables, branches, draw, incl, ang):
+    """make_perbin_likelihood with llh_ES_angle_perbin / llh_ES_poisson_perbin, and the day-night asymmetries of
+    derive_variables_from_chain.jl:236-258 (all cos-scatter bins summed; no CC asymmetry in the inclusive analysis)."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    t = branches(tables, incl, ang)
+    data = O.asimov_data(t)
+    p = draw(tables, 5, seed=400 + 10 * incl + ang)
+    p[4, 9] = 2.2                                              # one out-of-bounds earth norm: per-bin terms are -Inf
+    with SolarOscEngine(t, data=data) as e:
+        pb = e.eval_perbin(p)
+        a_es, a_cc = e.eval_asymmetry(p)
+    idx_es, idx_cc = int(t["index_es"]), int(t["index_cc"])
+    for i in range(4):
+        r = O.propagate_samples(p[i], t)
+        ref = dict(ES_day=_perbin_ref(r["ES_day"], data["ES_day"], idx_es, 1 if ang else 0),
+                   ES_night=_perbin_ref(r["ES_night"], data["ES_night"], idx_es, 1),
+                   CC_day=_perbin_ref(r["CC_day"], data["CC_day"], idx_cc, 0),
+                   CC_night=_perbin_ref(r["CC_night"], data["CC_night"], idx_cc, 1))
+        if incl == 1:                                          # use_CC is false: the CC arrays stay zero
+            ref["CC_day"][:], ref["CC_night"][:] = 0.0, 0.0
+        for k, b in ref.items():
+            a = pb[k][i]
+            assert a.shape == b.shape, k
+            assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)) < 1e-9, k
+        bg_es = r["BG_ES_tot"][idx_es - 1:].sum()
+        d = (r["ES_day"][:, idx_es - 1:] if ang else r["ES_day"][idx_es - 1:]).sum() - 0.5 * bg_es
+        n = r["ES_night"][:, idx_es - 1:].sum() - 0.5 * bg_es
+        assert abs(a_es[i] - 2 * (d - n) / (d + n)) < 1e-9
+        if incl == 1:
+            assert a_cc[i] == 0.0
+        else:
+            bg_cc = r["BG_CC_tot"][idx_cc - 1:].sum()
+            d = r["CC_day"][idx_cc - 1:].sum() - 0.5 * bg_cc
+            n = r["CC_night"][:, idx_cc - 1:].sum() - 0.5 * bg_cc
+            assert abs(a_cc[i] - 2 * (d - n) / (d + n)) < 1e-9
+    assert np.all(pb["ES_night"][4] == -np.inf) and np.all(pb["ES_day"][4] == -np.inf)
