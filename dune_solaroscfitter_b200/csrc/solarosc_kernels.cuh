@@ -107,7 +107,8 @@ __host__ __device__ inline size_t fold_vec_doubles(int n_etrue, int max_ereco) {
     return (size_t)2 * 4 * fold_kt(n_etrue) + (size_t)4 * 8 * ((max_ereco + 7) / 8);
 }
 __host__ __device__ inline size_t fold_scratch_doubles(int n_etrue, int max_ereco) {
-    return fold_vec_doubles(n_etrue, max_ereco) + kWarps + (kWarps + 1) / 2;
+    // an even number of doubles: the path tables behind the scratch are read with 16-byte loads
+    return (fold_vec_doubles(n_etrue, max_ereco) + kWarps + (kWarps + 1) / 2 + 1) & ~(size_t)1;
 }
 __host__ __device__ inline size_t rates_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
     return sizeof(double) * (fold_p_doubles(n_etrue, 1 + n_cosz) + fold_scratch_doubles(n_etrue, max_ereco));
