@@ -924,7 +924,7 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
                           double* mom_es, double* mom_cc, double* bg_mom_es, double* bg_mom_cc, double* scalars) {
     return guarded(h, [&]() {
         REQUIRE(params && weights, "params and weights must not be NULL");
-        REQUIRE(!h->gen, "derived-mode reductions serve the exclusive, non-angular analysis only");
+        REQUIRE(!h->T.det[det < 0 || det >= h->T.n_det ? 0 : det].ang, "derived-mode reductions do not cover the angular ES reconstruction");
         REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
         check_data(h, det);
         const DevTables& T = h->T;
@@ -964,7 +964,9 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             {   // rates with row-major night arrays whatever the handle's host layout is
                 RatesLaunch L = rates_launch(h, nb, 1, det);
                 L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
-                rates_kernel<kModeRates><<<nb, kThreads, rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco), h->stream>>>(T, L, h->d_params, h->d_osc, O);
+                const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GenLaunch{}, h->d_params, h->d_osc, O);
+                else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, h->d_params, h->d_osc, O);
                 CK(cudaGetLastError());
                 ++h->launches;
             }

@@ -84,8 +84,8 @@ enum {
  * With angular != 0 every ES array gains the cos-scatter axis, in the reference's index order: ES day is
  * (n_cos, n_ereco_es), ES night (n_cos, n_ereco_es, n_cosz) -- row-major [c][j] and [c][j][z] when col_major == 0,
  * [j][c] and [z][j][c] when col_major == 1 -- for obs_es_* and for the es_day / es_night outputs of
- * solarosc_eval_rates and solarosc_eval_perbin.  solarosc_eval_derived and solarosc_eval_llh_grad serve the
- * exclusive, non-angular branch only and return SOLAROSC_ERR_ARG otherwise.
+ * solarosc_eval_rates and solarosc_eval_perbin.  solarosc_eval_derived does not cover the angular arrays and
+ * solarosc_eval_llh_grad serves the exclusive, non-angular branch only: they return SOLAROSC_ERR_ARG otherwise.
  */
 typedef struct solarosc_detector_ext {
     int32_t inclusive;                  /* 0 exclusive, 1 inclusive_analysis, 2 semi_inclusive_analysis  */

@@ -98,9 +98,9 @@ def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw)
     with SolarOscEngine(t, data=data) as e:
         a = e.eval_rates(p)
         la = e.eval_llh(p)
-        with pytest.raises(SolarOscError):             # gradient and derived-mode sums: exclusive, non-angular analysis only
+        with pytest.raises(SolarOscError):             # the gradient entry serves the exclusive, non-angular analysis only
             e.eval_llh_grad(p)
-        with pytest.raises(SolarOscError):
+        with pytest.raises(SolarOscError):             # and the derived-mode sums do not cover the angular arrays
             e.eval_derived(p, np.ones(len(p)))
     # the same tables and data as Julia lays them out (column-major: numpy views with reversed shapes)
     tj = dict(t)
@@ -166,3 +166,26 @@ def test_perbin_and_asymmetry_of_the_branches(tables, branches, draw, incl, ang)
             n = r["CC_night"][:, idx_cc - 1:].sum() - 0.5 * bg_cc
             assert abs(a_cc[i] - 2 * (d - n) / (d + n)) < 1e-9
     assert np.all(pb["ES_night"][4] == -np.inf) and np.all(pb["ES_day"][4] == -np.inf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("incl", [1, 2])
+def test_derived_sums_of_the_non_angular_branches(tables, branches, draw, incl):
+    """solarosc_eval_derived on an inclusive / semi-inclusive detector: the rate moments are the branch's rates."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    t = branches(tables, incl, 0)
+    data = O.asimov_data(t)
+    p = draw(tables, 40, seed=500 + incl)
+    w = np.random.default_rng(incl).integers(1, 4, 40).astype(float)
+    with SolarOscEngine(t, data=data) as e:
+        got = e.eval_derived(p, w)
+        rates = e.eval_rates(p)
+        pb = e.eval_perbin(p)
+    k = int(t["index_es"]) - 1
+    m1 = np.einsum("i,ijk->jk", w, rates["ES_night"])
+    assert np.max(np.abs(got["mom_ES"][0][1:, k:] - m1[:, k:]) / m1[:, k:]) < 1e-12
+    assert np.all(got["mom_ES"][0][:, :k] == 0)
+    s1 = np.einsum("i,ijk->jk", w, pb["CC_night"])
+    assert np.max(np.abs(got["mom_CC"][2][1:] - s1)) <= 1e-9 * max(1.0, np.max(np.abs(s1)))
+    if incl == 1:
+        assert np.all(got["mom_CC"][:2] == 0)                   # the CC arrays are zero in the inclusive analysis
