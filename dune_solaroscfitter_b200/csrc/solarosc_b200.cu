@@ -171,6 +171,20 @@ void upload_data(solarosc_handle* h, int d, const double* es_day, const double* 
                     ol[2 * o] = m; ol[2 * o + 1] = m > 0.0 ? std::log(m) : 0.0;
                 }
         CK(cudaMemcpy(h->d_ol_ang[d], ol.data(), ol.size() * sizeof(double), cudaMemcpyHostToDevice));
+        // Poisson terms of the cos-scatter bins whose expectation is identically 0 (likelihood_statistical.jl:16-24 at e = 0)
+        DevDetector& D = h->T.det[d];
+        std::vector<bool> live(nC, false);
+        for (int k = 0; k < D.n_cos_live; ++k) live[D.cos_live[k]] = true;
+        const double e0 = 0.5 * (0.0 + 1e-9 + std::sqrt((0.0 - 1e-9) * (0.0 - 1e-9) + 1e-18));
+        double acc = 0.0;
+        for (int row = 0; row <= nZ; ++row)
+            for (int j = D.index_es - 1; j < nR; ++j)
+                for (int c = 0; c < nC; ++c) {
+                    if (live[c]) continue;
+                    const double m = ol[2 * (((size_t)row * nR + j) * nC + c)];
+                    acc += m > 0.0 ? e0 - m + m * (std::log(m) - std::log(e0)) : e0;
+                }
+        D.llh_dead_const = acc;
     } else {
         pack(es_day, es_night, h->n_es[d], h->d_obs_es[d], h->d_log_es[d], h->d_ol_es[d]);
     }
@@ -366,6 +380,13 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
                     for (int j = 0; j < D.n_es; ++j)
                         for (int cs = 0; cs < D.n_cos; ++cs) { sa[j] += am[(size_t)j * D.n_cos + cs]; sb[j] += bm[(size_t)j * D.n_cos + cs]; }
                     D.ang_sa = h->upload_vec(sa); D.ang_sb = h->upload_vec(sb);
+                    REQUIRE(D.n_cos <= kMaxCos, "too many cos-scatter bins");
+                    D.n_cos_live = 0;
+                    for (int cs = 0; cs < D.n_cos; ++cs) {
+                        bool live = false;
+                        for (int j = 0; j < D.n_es; ++j) live |= am[(size_t)j * D.n_cos + cs] != 0.0 || bm[(size_t)j * D.n_cos + cs] != 0.0;
+                        if (live) D.cos_live[D.n_cos_live++] = (unsigned char)cs;
+                    }
                 }
             }
             h->n_cos[d] = D.ang ? D.n_cos : 1;

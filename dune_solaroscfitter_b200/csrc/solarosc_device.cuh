@@ -20,6 +20,7 @@ constexpr double kPhaseQT = kPhase * 0.63661977236758134308;   // the same rate 
 constexpr double kDm31 = 2.5e-3;                  // reference osc.jl:44 (theta23, deltaCP drop out of P1e)
 constexpr int kMaxDet = 4;
 constexpr int kMaxFoldTasks = 48;
+constexpr int kMaxCos = 64;
 
 // one applied layer step: 0-based layer and length [km]; 16 bytes so a step's metadata is one load
 struct __align__(16) Seg {
@@ -55,6 +56,12 @@ struct DevDetector {
     const double *yp8, *yph, *yc8, *ych;  // mis-identified ES in the CC bins: matrices (layout of b8) and constants
     const double *angm, *bgang;           // [n_es][n_cos]: mask_c ES.angular[c][j], BG.angular[c][j]
     const double *ang_sa, *ang_sb;        // [n_es]: their sums over the cos-scatter bins
+    // cos-scatter bins with a non-zero table entry somewhere (the others -- the hemisphere the cos cut removes -- have an
+    // expectation of exactly 0 whatever the parameters: their Poisson terms depend on the data only and are summed once,
+    // at set_data, into llh_dead_const)
+    int n_cos_live;
+    unsigned char cos_live[kMaxCos];
+    double llh_dead_const;
     const double2* ol_es_ang;             // angular ES data (m, log m), [1 + n_cosz][n_es][n_cos]
 };
 

@@ -269,7 +269,8 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                             if (8 * (m0 + c) + fg == 0) d_es += s01; else n_es += s01;
                         }
                     } else
-                    for (int cs = 0; cs < ncos; ++cs) {
+                    for (int ci = 0; ci < (MODE == kModeLlh ? D.n_cos_live : ncos); ++ci) {
+                        const int cs = MODE == kModeLlh ? (int)D.cos_live[ci] : ci;   // the likelihood skips the bins the cut empties
                         const double ga0 = __ldg(am0 + cs), ga1 = __ldg(am1 + cs), gb0 = __ldg(bm0 + cs), gb1 = __ldg(bm1 + cs);
                         if (MODE == kModeLlh) {
                             double2 o0[kMCg], o1[kMCg];
@@ -332,6 +333,7 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
                 }
             }
         }
+        if (MODE == kModeLlh && D.ang && es_on && threadIdx.x == 0) part += D.llh_dead_const;
         total += part;
     }
     if (MODE != kModeLlh) return;
