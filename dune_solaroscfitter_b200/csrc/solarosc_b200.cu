@@ -514,6 +514,8 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     if (h->fused_ok) {
         CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         CK(cudaFuncSetAttribute(llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(gen_llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(gen_llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         // One CTA per oscillation point by default: measured 8 % faster than a persistent grid of 2 CTAs per SM
         // (starting the second CTA of each SM half a period late made no difference, so it is not a phase effect).
         h->fused_grid = 1 << 30;
@@ -589,6 +591,17 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
 bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid,
                 int mode = kModeLlh, int det_only = -1) {
     const int n_osc = n / group;
+    if (h->fused_ok && h->use_fused && h->gen && n_osc >= h->sm_count) {
+        // inclusive / semi-inclusive / angular detectors: the same fusion with the general fold
+        const RatesLaunch L = rates_launch(h, n, group, det_only);
+        const int grid = std::min(n_osc, h->fused_grid);
+        if (mode == kModeLlh) gen_llh_kernel<kModeLlh><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, GenLaunch{}, d_params, O);
+        else gen_llh_kernel<kModeAsym><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, GenLaunch{}, d_params, O);
+        CK(cudaGetLastError());
+        ++h->launches;
+        if (mid) CK(cudaEventRecord(mid, st));
+        return true;
+    }
     if (h->fused_ok && h->use_fused && !h->gen && n_osc >= h->sm_count) {
         const RatesLaunch L = rates_launch(h, n, group, det_only);
         const int grid = std::min(n_osc, h->fused_grid);

@@ -82,30 +82,13 @@ __device__ __forceinline__ void gen_fold_vectors(const DevTables& T, const DevDe
     }
 }
 
+// K3 + K4 + K5 of one parameter point on the probability tile (p8s, phs: [rows][ldp] per process in shared memory).
+// Starts with a barrier (orders the tile and the scratch), like fold_stage.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, SOLAROSC_RATES_MINBLOCKS)
-gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const double* __restrict__ params,
-           const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
-    extern __shared__ __align__(16) double smem[];
-    const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+__device__ __forceinline__ void gen_fold_stage(const DevTables& T, const RatesLaunch& L, const GenLaunch& GL, const double* __restrict__ p,
+                                               size_t b, const double* p8s, const double* phs, int ldp, double* scr, const RatesOut& O) {
+    const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ;
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
-    double* p8s = smem;
-    double* phs = p8s + (size_t)rows * ldp;
-    double* scr = p8s + fold_p_doubles(nT, nrow);
-    const size_t b = blockIdx.x;
-    const double* src = osc + (b / L.group) * 2 * nrow * nT;
-    const double* p = params + b * L.param_stride;
-    fold_zero_padding(p8s, nT, rows, ldp);
-    {
-        const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
-        int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;
-        while (row < nrow) {
-            p8s[row * ldp + i] = src[row * nT + i];
-            phs[row * ldp + i] = src[(nrow + row) * nT + i];
-            i += dr; row += dq;
-            if (i >= nT) { i -= nT; ++row; }
-        }
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane >> 2, ft = lane & 3;
     double* scale = scr;
     double* red = scr + fold_vec_doubles(nT, L.max_ereco);
@@ -352,6 +335,60 @@ gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const dou
         else if (lnl != lnl) f |= (f & SOLAROSC_FLAG_NEG_ERROR) ? 0u : SOLAROSC_FLAG_NONFINITE;
         O.lnl[b] = lnl;
         if (O.flags) O.flags[b] = f;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, SOLAROSC_RATES_MINBLOCKS)
+gen_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const double* __restrict__ params,
+           const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
+    extern __shared__ __align__(16) double smem[];
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    double* p8s = smem;
+    double* phs = p8s + (size_t)rows * ldp;
+    double* scr = p8s + fold_p_doubles(nT, nrow);
+    const size_t b = blockIdx.x;
+    const double* src = osc + (b / L.group) * 2 * nrow * nT;
+    fold_zero_padding(p8s, nT, rows, ldp);
+    {
+        const int dq = (int)blockDim.x / nT, dr = (int)blockDim.x - dq * nT;
+        int row = (int)threadIdx.x / nT, i = (int)threadIdx.x - row * nT;
+        while (row < nrow) {
+            p8s[row * ldp + i] = src[row * nT + i];
+            phs[row * ldp + i] = src[(nrow + row) * nT + i];
+            i += dr; row += dq;
+            if (i >= nT) { i -= nT; ++row; }
+        }
+    }
+    gen_fold_stage<MODE>(T, L, GL, params + b * L.param_stride, b, p8s, phs, ldp, scr, O);
+}
+
+// Fused variant (likelihood and asymmetry): K1 + K2 into the shared-memory probability tile as in llh_kernel, then the
+// general fold for every point of the group.  Same shared-memory layout as llh_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, SOLAROSC_LLH_MINBLOCKS)
+gen_llh_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const double* __restrict__ params, RatesOut O) {
+    extern __shared__ __align__(16) double smem[];
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, ldp = fold_ldp(nT);
+    const int cbs = L.osc_cb;
+    double* tbl = smem;
+    double* msw = smem + (size_t)kEntry * T.n_ltbl * 2 * cbs;
+    double* p8s = smem + osc_smem_doubles(T.n_ltbl, cbs);
+    double* phs = p8s + (size_t)nrow * ldp;
+    double* scr = phs + (size_t)nrow * ldp;
+    const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), true);
+    fold_zero_padding(p8s, nT, nrow, ldp);
+    const int n_osc = L.n_points / L.group;
+    for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
+        const double* po = params + (size_t)g * L.group * L.param_stride;
+        for (int i0 = 0; i0 < nT; i0 += cbs) {
+            if (i0 > 0 || g != (int)blockIdx.x) __syncthreads();   // the previous table / tile are no longer being read
+            osc_stage<true>(T, G, po, i0, min(cbs, nT - i0), cbs, tbl, msw, nullptr, SmemSink{p8s, phs, ldp});
+        }
+        for (int q = 0; q < L.group; ++q) {
+            const size_t b = (size_t)g * L.group + q;
+            gen_fold_stage<MODE>(T, L, GL, params + b * L.param_stride, b, p8s, phs, ldp, scr, O);
+        }
     }
 }
 
