@@ -77,6 +77,13 @@ struct solarosc_handle {
     double* d_lnl2[2]{};
     uint32_t* d_flags2[2]{};
     double* h_lnl2[2]{};         // pinned staging of the results of one chunk, double-buffered
+    // small batches (MCMC steps of a few chains) replay one captured CUDA graph: H2D, the kernels and both D2H copies
+    // become a single launch.  Keyed by (n, group); inputs go through a pinned staging row block.
+    double* h_params_pin = nullptr;
+    cudaGraphExec_t small_graph = nullptr;
+    size_t small_n = 0, small_group = 0;
+    int small_launches = 0;
+    bool small_fused = false;
     uint32_t* h_flags2[2]{};
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
     double* d_gradws = nullptr;  // gradient path: probabilities of each point and its shifted copies, then the gradients
@@ -647,6 +654,51 @@ int guarded(solarosc_handle* h, F&& body) {
     }
 }
 
+// Small batches are launch- and latency-bound: the whole step (H2D of the rows, oscillation and fold kernels, D2H of lnL
+// and flags) is captured once into a CUDA graph and replayed with one launch per call.
+constexpr size_t kSmallBatch = 256;
+int eval_llh_small(solarosc_handle* h, const double* params, size_t n, size_t group, double* out, uint32_t* flags) {
+    if (!h->h_params_pin) CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_params_pin), kSmallBatch * (size_t)h->P * sizeof(double)));
+    if (!h->small_graph || h->small_n != n || h->small_group != group) {
+        if (h->small_graph) { cudaGraphExecDestroy(h->small_graph); h->small_graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            CK(cudaMemcpyAsync(h->d_params2[0], h->h_params_pin, n * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            RatesOut O{};
+            O.lnl = h->d_lnl2[0]; O.flags = h->d_flags2[0];
+            h->launches = 0;
+            h->small_fused = launch_llh(h, h->d_params2[0], (int)n, (int)group, O, h->stream, nullptr);
+            h->small_launches = h->launches;
+            CK(cudaMemcpyAsync(h->h_lnl2[0], h->d_lnl2[0], n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(h->h_flags2[0], h->d_flags2[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        } catch (...) {
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CK(cudaStreamEndCapture(h->stream, &g));
+        const cudaError_t e = cudaGraphInstantiate(&h->small_graph, g, 0);
+        cudaGraphDestroy(g);
+        CK(e);
+        h->small_n = n; h->small_group = group;
+    }
+    std::memcpy(h->h_params_pin, params, n * h->P * sizeof(double));
+    CK(cudaGraphLaunch(h->small_graph, h->stream));
+    h->launches = h->small_launches;
+    h->last_fused = h->small_fused;
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->h_lnl2[0], n * sizeof(double));
+    bool neg = false;
+    for (size_t i = 0; i < n; ++i) neg |= (h->h_flags2[0][i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+    if (flags) std::memcpy(flags, h->h_flags2[0], n * sizeof(uint32_t));
+    if (neg) {
+        h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
+        return SOLAROSC_ERR_NEGATIVE_RATE;
+    }
+    return SOLAROSC_OK;
+}
+
 // Host-buffer likelihood evaluation.  Three streams form a pipeline over chunks: H2D of chunk c+1
 // (straight from the caller's buffer: asynchronous when it is pinned, staged by the driver when
 // pageable) overlaps the two kernels of chunk c and the D2H of chunk c-1 into pinned staging; the host thread
@@ -659,6 +711,7 @@ int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t gro
     h->launches = 0;
     h->tev_used = 0;
     h->tev_stream = h->stream;
+    if (n <= kSmallBatch && n <= (size_t)h->chunk && !h->timing) return eval_llh_small(h, params, n, group, out, flags);
     // results come back through two pinned staging slots and are handed to the caller's (possibly pageable) arrays by
     // the host thread two chunks behind the GPU: every copy on the streams stays asynchronous
     const size_t step = ((size_t)h->chunk / group) * group;
@@ -839,6 +892,8 @@ void solarosc_destroy(solarosc_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_gradws) cudaFree(h->d_gradws);
+    if (h->small_graph) cudaGraphExecDestroy(h->small_graph);
+    if (h->h_params_pin) cudaFreeHost(h->h_params_pin);
     for (int i = 0; i < 2; ++i) {
         if (h->h_lnl2[i]) cudaFreeHost(h->h_lnl2[i]);
         if (h->h_flags2[i]) cudaFreeHost(h->h_flags2[i]);
@@ -866,6 +921,10 @@ int solarosc_set_data(solarosc_handle* h, int det, const double* es_day, const d
         REQUIRE(es_day && es_night && cc_day && cc_night, "data pointers must not be NULL");
         CK(cudaStreamSynchronize(h->stream));
         upload_data(h, det, es_day, es_night, cc_day, cc_night);
+        if (h->small_graph) {   // the captured kernel arguments carry data-dependent constants
+            cudaGraphExecDestroy(h->small_graph);
+            h->small_graph = nullptr;
+        }
         return (int)SOLAROSC_OK;
     });
 }
