@@ -130,3 +130,23 @@ def test_other_binnings_of_the_branches(incl, ang):
             assert np.max(np.abs(rates[k][i] - ref[k]) / np.where(scale > 0, scale, 1.0)) < 1e-9, k
         assert abs(2 * lnl[i] - 2 * O.total_llh(p[i], t, data)) < 1e-6
     assert np.max(np.abs(big.reshape(60, -1) - lnl[None, :])) < 1e-8
+
+
+@pytest.mark.parametrize("shape", [SHAPES[1], SHAPES[3]])
+def test_gradient_on_other_binnings(shape):
+    """solarosc_eval_llh_grad on odd binnings: every column against a central difference of the value."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    t = synthetic_tables(31 + shape[0], *shape)
+    data = O.asimov_data(t)
+    p = draws(t, 3, seed=5)
+    with SolarOscEngine(t, data=data) as e:
+        lnl, g = e.eval_llh_grad(p)
+        assert np.max(np.abs(lnl - e.eval_llh(p))) < 5e-7
+        used = [c for c in range(p.shape[1])]
+        for c in used:
+            h = 1e-6 * max(abs(p[0, c]), 1e-3) if c != 2 else 1e-9
+            pp, pm = p.copy(), p.copy()
+            pp[:, c] += h; pm[:, c] -= h
+            fd = (e.eval_llh(pp) - e.eval_llh(pm)) / (2 * h)
+            scale = np.maximum(np.abs(fd), 1e-3 * np.max(np.abs(g[:, c])) + 1e-12)
+            assert np.max(np.abs(g[:, c] - fd) / scale) < 2e-3, (c, g[:, c], fd)
