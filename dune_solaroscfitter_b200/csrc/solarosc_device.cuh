@@ -218,7 +218,7 @@ SOLAROSC_HD void sincos_qt(double len, double kq, double& s, double& c) {
 //     S = diag(0, dm21, dm31) + a * u u^T  - a*I,     a = rho*E,  u = (c12 c13, s12 c13, s13),
 // and P1e = |<nu_1| prod_k exp(-i S_k t_k) |u>|^2 does not depend on theta23 or deltaCP at all.
 // S is a rank-one update of a diagonal matrix: eigenvalues from the trigonometric solution of the
-// characteristic cubic, refined through the secular equation; eigenvectors from
+// characteristic cubic, each polished by a Newton step in gap form (below); eigenvectors from
 // v_i[j] ~ u_j * prod_{k != j} (mu_i - m_k) (no divisions, well defined when a or some u_j
 // vanish).  Only eigenvalue differences are returned (the common phase drops out of |amplitude|^2).
 // q[3*j+i] = component j of eigenvector i.
@@ -258,20 +258,29 @@ SOLAROSC_HD void eig_rank_one(double d21, double d31, double a, double u1, doubl
         t = fmin(mu[1], mu[2]); mu[2] = fmax(mu[1], mu[2]); mu[1] = t;
         t = fmin(mu[0], mu[1]); mu[1] = fmax(mu[0], mu[1]); mu[0] = t;
     }
-    // Root i sits next to pole m_i (interlacing).  Its shift delta_i = mu_i - m_i is re-derived from
-    // the secular equation 1 + a sum_k u_k^2/(m_k - mu) = 0, solved for the i-th term:
-    //     delta_i = a u_i^2 g_k g_l / (g_k g_l + a (u_k^2 g_l + u_l^2 g_k)),   g_x = m_x - mu_i,
-    // an identity that only uses the well-conditioned gaps to the OTHER poles, so delta_i keeps
-    // full relative accuracy when a u_i^2 is far below the rounding noise of the cubic's roots
-    // (weak matter, tiny theta13) and is exactly 0 when state i decouples (u_i = 0).
+    // Root i sits between pole m_i and the next one (interlacing).  Its gaps to the poles, g_x = m_x - mu_i, are
+    // polished with one Newton step on the characteristic polynomial written in those gaps,
+    //     h(g_i) = g_i A + a u_i^2 B,   A = g_k g_l + a (u_k^2 g_l + u_l^2 g_k),   B = g_k g_l
+    // (all three gaps move together with mu_i).  In gap form every product is formed from small, accurately known
+    // factors, so the step converges quadratically to full RELATIVE accuracy of each gap from the cubic's roots, whose
+    // error is absolute: when a u_i^2 is far below the rounding noise of the cubic (weak matter, tiny theta13) h is
+    // linear in g_i and the step lands on g_i = -a u_i^2 B / A; when the matter term exceeds dm21 and two roots share
+    // the neighbourhood of two close poles it still converges, where the fixed-point form of the same equation would
+    // amplify the cubic's error by u_i^2 / u_k^2.  A decoupled state (u_i = 0) keeps its pole.
     double dl[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const int k = (i == 0) ? 1 : 0, l = (i == 2) ? 1 : 2;
-        const double gk = m[k] - mu[i], gl = m[l] - mu[i];
-        const double den = fma(a, fma(u[k] * u[k], gl, u[l] * u[l] * gk), gk * gl);
-        const double num = a * u[i] * u[i] * gk * gl;
-        const double d = (den != 0.0) ? num * rcp(den) : mu[i] - m[i];
+        double gi = m[i] - mu[i], gk = m[k] - mu[i], gl = m[l] - mu[i];
+        const double ui2 = u[i] * u[i], uk2 = u[k] * u[k], ul2 = u[l] * u[l];
+        const double B = gk * gl, Bp = gk + gl;
+        const double A = fma(a, fma(uk2, gl, ul2 * gk), B), Ap = fma(a, uk2 + ul2, Bp);
+        const double aui2 = a * ui2;
+        const double h = fma(gi, A, aui2 * B), hp = fma(gi, Ap, fma(aui2, Bp, A));
+        // (an exactly decoupled state sits exactly on its pole: g_i = 0, and its eigenvector is the unit vector below)
+        const double dg = (aui2 == 0.0) ? gi : ((hp != 0.0) ? h * rcp(hp) : 0.0);
+        gi -= dg; gk -= dg; gl -= dg;
+        const double d = -gi;
         dl[i] = d;
         // eigenvector: v[j] ~ u_j prod_{x != j} (mu_i - m_x)
         const double vi = u[i] * (gk * gl), vk = -u[k] * (d * gl), vl = -u[l] * (d * gk);

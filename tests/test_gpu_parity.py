@@ -235,3 +235,45 @@ def test_device_resident_entry(engine, tables, draw):
                            stream_ptr=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_parameter_corners(engine, coracle, tables):
+    """Degenerate and extreme parameter points (the cases of tests/test_host_math.py plus flux / cross-section /
+    background extremes) through the full GPU path: P1e, rates and -2lnL against the oracle."""
+    truth = np.asarray(tables["truth"], dtype=float)
+    corners = [
+        dict(c0=0.454, c1=0.0, c2=8.6e-5),                      # theta13 = 0: the third state decouples exactly
+        dict(c0=0.0, c1=0.0232, c2=1.4e-4),                     # theta12 = 0
+        dict(c0=1.0, c1=0.0095, c2=1.5e-4),                     # theta12 = pi/2
+        dict(c0=0.32, c1=0.0317, c2=2e-5, norms=2.0),           # strongest matter effect inside the priors
+        dict(c0=0.462, c1=1e-12, c2=1.9e-4),                    # shift far below the rounding noise of the cubic
+        dict(c0=0.4, c1=0.25, c2=4e-5),                         # llhScan.jl's theta13 upper limit
+        dict(c0=0.2, c1=1e-4, c2=2.08e-4, norms=0.5),
+        dict(c0=0.307, c1=0.0224, c2=6e-5, norms=0.0),          # vacuum: all earth norms 0
+        dict(c0=0.307, c1=0.0224, c2=1e-6),                     # dm21 far below the matter potential
+        dict(c0=0.307, c1=0.0224, c2=1e-3),                     # dm21 close to dm31
+        dict(c0=1.3, c1=-0.2, c2=6e-5),                         # out-of-range mixings are clamped (propagation_osc.jl:30-36)
+        dict(c0=0.307, c1=0.0224, c2=6e-5, c3=0.0, c4=0.0),     # no signal at all: backgrounds only
+        dict(c0=0.307, c1=0.0224, c2=6e-5, c5=2.0, c6=0.5, c7=-0.3),
+        dict(c0=0.307, c1=0.0224, c2=6e-5, c14=0.0, c17=0.0, c18=1e-5),
+    ]
+    p = np.tile(truth, (len(corners), 1))
+    for i, c in enumerate(corners):
+        for k, v in c.items():
+            if k == "norms":
+                p[i, 8:14] = v
+            else:
+                p[i, int(k[1:])] = v
+    got, fl = engine.eval_llh(p, return_flags=True)
+    ref, rfl = coracle.eval_llh(p)
+    assert np.array_equal(fl, rfl)
+    assert np.max(np.abs(2 * got - 2 * ref)) < 1e-6
+    big = engine.eval_llh(np.tile(p, (12, 1)))                 # the fused kernel
+    assert np.max(np.abs(big.reshape(12, -1) - got[None, :])) < 1e-7
+    p1e = engine.eval_p1e(p)
+    _, rp1e = coracle.eval_oscprobs(p, want_p1e=True)
+    assert np.max(np.abs(p1e - rp1e)) < 5e-12
+    r, rr = engine.eval_rates(p), coracle.eval_rates(p)
+    for k in ("ES_day", "ES_night", "CC_day", "CC_night"):
+        scale = np.maximum(np.abs(rr[k]), 1e-9 * np.max(np.abs(rr[k])))
+        assert np.max(np.abs(r[k] - rr[k]) / scale) < 1e-9, k
