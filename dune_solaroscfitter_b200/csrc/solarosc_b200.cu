@@ -56,6 +56,7 @@ struct solarosc_handle {
     int max_ereco = 0;
     int n_es[kMaxDet]{}, n_cc[kMaxDet]{};
     int n_cos[kMaxDet]{};        // cos-scatter bins of the ES arrays (1 unless the detector uses the angular reconstruction)
+    bool fold_fine_ok = false;   // every detector has a fine work list for the grouped fold
     bool gen = false;            // some detector runs an inclusive / semi-inclusive / angular branch: gen_kernel serves every call
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t s_in = nullptr, s_out = nullptr;  // H2D / D2H of the host-buffer pipeline
@@ -519,8 +520,17 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         h->fused_ok = h->fused_seg && h->fused_smem <= per_cta_max;   // the fused kernel reads the path tables from shared memory
     }
     if (h->fused_ok) {
-        CK(cudaFuncSetAttribute(llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
-        CK(cudaFuncSetAttribute(llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(llh_kernel<kModeLlh, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(llh_kernel<kModeLlh, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(llh_kernel<kModeAsym, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        // grouped evaluation cuts the fold into finer work items when every detector has a work list (fold_stage)
+        h->fold_fine_ok = true;
+        for (int d = 0; d < T.n_det; ++d) {
+            const DevDetector& D = T.det[d];
+            const int mt = (1 + T.n_cosz + 7) / 8, nb = D.nte_thr + D.ntc_thr;
+            const int na = mt / kMCa, nbm = (mt - kMCa * na + kMCb - 1) / kMCb;
+            h->fold_fine_ok = h->fold_fine_ok && D.fold_ntask > 0 && D.fold_ntask == nb * (na + nbm);
+        }
         CK(cudaFuncSetAttribute(gen_llh_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         CK(cudaFuncSetAttribute(gen_llh_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         // One CTA per oscillation point by default: measured 8 % faster than a persistent grid of 2 CTAs per SM
@@ -612,8 +622,9 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
     if (h->fused_ok && h->use_fused && !h->gen && n_osc >= h->sm_count) {
         const RatesLaunch L = rates_launch(h, n, group, det_only);
         const int grid = std::min(n_osc, h->fused_grid);
-        if (mode == kModeLlh) llh_kernel<kModeLlh><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
-        else llh_kernel<kModeAsym><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        if (mode == kModeLlh && group > 1 && h->fold_fine_ok) llh_kernel<kModeLlh, true><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        else if (mode == kModeLlh) llh_kernel<kModeLlh, false><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        else llh_kernel<kModeAsym, false><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         CK(cudaGetLastError());
         ++h->launches;
         if (mid) CK(cudaEventRecord(mid, st));

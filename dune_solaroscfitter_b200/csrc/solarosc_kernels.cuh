@@ -682,7 +682,7 @@ struct FoldTask {
     }
 };
 
-template <int MODE>
+template <int MODE, bool FINE = false>
 __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch& L, const double* __restrict__ p, size_t b,
                                            const double* p8s, const double* phs, int ldp, double* scr,
                                            const RatesOut& O, bool vectors_ready = false) {
@@ -751,7 +751,7 @@ __device__ __forceinline__ void fold_stage(const DevTables& T, const RatesLaunch
         const int nb = bte + btc;
         const int na = mt / kMCa, nbm = (mt - kMCa * na + kMCb - 1) / kMCb;
         const int ntask = nb * (na + nbm);
-        if (kThr && L.group > 1 && D.fold_ntask == ntask) {
+        if (FINE) {   // (a kernel of its own, llh_kernel<MODE, true>: the two arrangements do not share register allocation)
             for (int t = 0; t < ntask; ++t) {
                 if ((int)D.fold_owner[t] != warp) continue;
                 const bool big = t < nb * na;
@@ -852,7 +852,7 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
 // point: K1+K2 into the shared-memory probability tile, one energy chunk (L.osc_cb coarse bins) at a time so
 // that the eigen table stays small enough for several CTAs per SM, then K3+K4+K5 for each of the `group`
 // parameter points sharing it.  The oscillation probabilities never leave the SM.
-template <int MODE>
+template <int MODE, bool FINE>
 __global__ void __launch_bounds__(kThreads, SOLAROSC_LLH_MINBLOCKS)
 llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ params, RatesOut O) {
     extern __shared__ __align__(16) double smem[];
@@ -882,7 +882,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
         for (int q = 0; q < L.group; ++q) {
             const size_t b = (size_t)g * L.group + q;
             // fold_stage begins with a barrier, which also orders the probability tile after osc_stage
-            fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, q == 0);
+            fold_stage<MODE, FINE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O, q == 0);
         }
     }
 }
