@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "solarosc_grad.cuh"
+#include "solarosc_pipe.cuh"
 #include "solarosc_general.cuh"
 #include "solarosc_setup.cuh"
 
@@ -104,6 +105,16 @@ struct solarosc_handle {
     int launches = 0;
     bool use_fused = true;
     bool last_fused = false;
+    // pipe_kernel (solarosc_pipe.cuh): ticket pattern and fold items per (mode, group, detector), built on first use
+    struct PipePlan {
+        int mode, group, det_only;
+        bool ok;
+        PipeLaunch L;
+        size_t smem;
+    };
+    std::vector<PipePlan> pipe_plans;
+    bool use_pipe = true, pipe_all = false;
+    size_t smem_optin = 0;
 
     template <class Tp>
     Tp* dalloc(size_t n) {
@@ -222,6 +233,9 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     if (prop.major != 10) throw CudaFail{"libsolarosc_b200 holds sm_100a code only; this device is not compute capability 10.x"};
     h->sm_count = prop.multiProcessorCount;
     h->osc_smem_limit = std::min<size_t>(200 * 1024, prop.sharedMemPerBlockOptin);
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->use_pipe = std::getenv("SOLAROSC_NO_PIPE") == nullptr;   // A/B switches: the lock-step llh_kernel instead of pipe_kernel,
+    h->pipe_all = std::getenv("SOLAROSC_PIPE_ALL") != nullptr;  // and pipe_kernel for independent points too
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -519,6 +533,10 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         if (const char* e = std::getenv("SOLAROSC_LLH_EXTRA_SMEM")) h->fused_smem += (size_t)atoi(e);   // diagnostics: force fewer CTAs per SM
         h->fused_ok = h->fused_seg && h->fused_smem <= per_cta_max;   // the fused kernel reads the path tables from shared memory
     }
+    CK(cudaFuncSetAttribute(pipe_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncSetAttribute(pipe_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncSetAttribute(pipe_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncSetAttribute(pipe_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     if (h->fused_ok) {
         CK(cudaFuncSetAttribute(llh_kernel<kModeLlh, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         CK(cudaFuncSetAttribute(llh_kernel<kModeLlh, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
@@ -603,11 +621,115 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     ++h->launches;
 }
 
+// Ticket pattern and fold items of pipe_kernel for one (mode, group, detector) combination (solarosc_pipe.cuh).
+// Within the block of tickets of one step the propagation items P(n) are spread evenly and the eigen/MSW items
+// E(n+1) and fold items F(n-1) are spread over the middle of the block: their dependencies (items of the previous
+// block) have drained by then, and they are done before the next block's propagation asks for their results.
+const solarosc_handle::PipePlan* pipe_plan(solarosc_handle* h, int mode, int group, int det_only) {
+    for (const auto& pl : h->pipe_plans)
+        if (pl.mode == mode && pl.group == group && pl.det_only == det_only) return pl.ok ? &pl : nullptr;
+    const DevTables& T = h->T;
+    solarosc_handle::PipePlan pl{};
+    pl.mode = mode; pl.group = group; pl.det_only = det_only; pl.ok = false;
+    const bool thr = mode == kModeLlh || mode == kModeAsym;
+    const int nrow = 1 + T.n_cosz, mt = (nrow + 7) / 8;
+    std::vector<PipeFoldItem> items;
+    for (int d = 0; d < T.n_det; ++d) {
+        if (det_only >= 0 && d != det_only) continue;
+        const DevDetector& D = T.det[d];
+        const int nb = thr ? D.nte_thr + D.ntc_thr : (D.n_es + 7) / 8 + (D.n_cc + 7) / 8;
+        int per = kPipeNT;                             // row tiles per fold item
+        if (const char* e = std::getenv("SOLAROSC_PIPE_FTILES")) per = std::max(1, atoi(e));
+        for (int col = 0; col < nb; ++col)
+            for (int m0 = 0; m0 < mt; m0 += per)
+                items.push_back(PipeFoldItem{(unsigned char)d, (unsigned char)col, (unsigned char)m0, (unsigned char)std::min(per, mt - m0)});
+    }
+    PipeLaunch L{};
+    L.group = group; L.param_stride = h->P; L.det_only = det_only; L.max_ereco = h->max_ereco;
+    L.n_f = (int)items.size();
+    L.n_p = 1 + (T.n_cosz * T.n_etrue + 31) / 32;
+    L.n_eig = (2 * T.n_etrue * T.n_ltbl + 32 * kPipeEPL - 1) / (32 * kPipeEPL);
+    L.msw_per_item = T.fast ? 0 : 2;
+    L.n_e = L.n_eig + (T.fast ? 1 : (2 * T.n_etrue + L.msw_per_item - 1) / L.msw_per_item);
+    const int red = mode == kModeAsym ? 3 : 1;
+    const PipeSmem S = pipe_smem(T.n_ltbl, T.n_etrue, T.n_cosz, group, L.n_f, red, h->seg_bytes / sizeof(double));
+    pl.smem = S.total * sizeof(double);
+    const long long n_f_tot = (long long)group * L.n_f;
+    const bool fits = !h->gen && pl.smem <= h->smem_optin && group <= kPipeMaxGroup && n_f_tot < (1 << 14) && L.n_p < (1 << 14) &&
+                      mt <= 255 && L.n_f > 0 && T.n_sub >= 1;
+    if (fits) {
+        // Items of one kind are issued in clusters (all E items together, the F items in a few runs), so that the warps
+        // that draw them stream the same straight-line code at the same time and share its instruction-cache lines;
+        // scattered singly, every item fetched its 30 kB of code on its own (ncu: 33 % of the stalls were
+        // no_instructions).  The clusters sit evenly between runs of propagation items.
+        struct Tk { double key; unsigned short code; };
+        std::vector<Tk> tk;
+        int f_clusters = 1, e_clusters = 1;                                 // 0: scattered singly
+        if (const char* e = std::getenv("SOLAROSC_PIPE_FCLUSTERS")) f_clusters = std::max(0, atoi(e));
+        if (const char* e = std::getenv("SOLAROSC_PIPE_ECLUSTERS")) e_clusters = std::max(0, atoi(e));
+        const long long fc = f_clusters == 0 ? n_f_tot : std::min<long long>(f_clusters * (long long)group, n_f_tot);
+        const int ec = e_clusters == 0 ? L.n_e : std::min(e_clusters, L.n_e);
+        for (int i = 0; i < L.n_p; ++i) tk.push_back({(i + 0.5) / L.n_p, (unsigned short)((kPipeP << 14) | i)});
+        // E clusters over the first 45 % of the block (the next step's propagation waits for them longest), F clusters
+        // over 50 .. 90 %
+        for (int i = 0; i < L.n_e; ++i) {
+            const int c = (int)((long long)i * ec / L.n_e);
+            tk.push_back({0.05 + 0.40 * (c + 0.5) / ec + 1e-7 * i, (unsigned short)((kPipeE << 14) | i)});
+        }
+        for (long long i = 0; i < n_f_tot; ++i) {
+            const long long c = i * fc / n_f_tot;
+            tk.push_back({0.50 + 0.40 * (c + 0.5) / (double)fc + 1e-7 * (double)i, (unsigned short)((kPipeF << 14) | (int)i)});
+        }
+        std::stable_sort(tk.begin(), tk.end(), [](const Tk& a, const Tk& b) { return a.key < b.key; });
+        std::vector<unsigned short> pattern(tk.size());
+        for (size_t i = 0; i < tk.size(); ++i) pattern[i] = tk[i].code;
+        L.block_len = (int)pattern.size();
+        L.pattern = h->upload(pattern.data(), pattern.size());
+        L.fitems = h->upload(items.data(), items.size());
+        pl.ok = true;
+    }
+    pl.L = L;
+    h->pipe_plans.push_back(pl);
+    return pl.ok ? &h->pipe_plans.back() : nullptr;
+}
+
+bool launch_pipe(solarosc_handle* h, const double* d_params, int n, int group, int mode, int det_only, RatesOut O, cudaStream_t st,
+                 bool row_major = false) {
+    if (!h->use_pipe || !h->use_fused || h->gen) return false;
+    const int n_osc = n / group;
+    if (n_osc < h->sm_count) return false;
+    // Independent points (group == 1) stay with the lock-step llh_kernel: measured 7.8 M evaluations/s against 6.7 M for
+    // this kernel, whose ticket / dependency bookkeeping costs 23 % more instructions while the SM is co-limited by issue
+    // slots (profiles/r02_notes.md).  The pipeline pays where the fold dominates (grouped scan cells: 24.3 M against
+    // 21.8 M) and for the array outputs, which otherwise take the probability block through HBM.
+    if (mode == kModeLlh && group == 1 && !h->pipe_all) return false;
+    const solarosc_handle::PipePlan* pl = pipe_plan(h, mode, group, det_only);
+    if (!pl) return false;
+    PipeLaunch L = pl->L;
+    L.n_osc = n_osc;
+    const int d = det_only >= 0 ? det_only : 0;
+    const bool cm = h->cfg.col_major != 0 && !row_major;
+    L.s_row_es = cm ? 1 : h->n_es[d]; L.s_j_es = cm ? h->T.n_cosz : 1;
+    L.s_row_cc = cm ? 1 : h->n_cc[d]; L.s_j_cc = cm ? h->T.n_cosz : 1;
+    const int grid = std::min(n_osc, h->sm_count);
+    if (mode == kModeLlh) pipe_kernel<kModeLlh><<<grid, kPipeThreads, pl->smem, st>>>(h->T, L, d_params, O);
+    else if (mode == kModeAsym) pipe_kernel<kModeAsym><<<grid, kPipeThreads, pl->smem, st>>>(h->T, L, d_params, O);
+    else if (mode == kModeRates) pipe_kernel<kModeRates><<<grid, kPipeThreads, pl->smem, st>>>(h->T, L, d_params, O);
+    else pipe_kernel<kModePerbin><<<grid, kPipeThreads, pl->smem, st>>>(h->T, L, d_params, O);
+    CK(cudaGetLastError());
+    ++h->launches;
+    return true;
+}
+
 // lnL of n points; the fused kernel when the batch fills the GPU, otherwise the energy-split
 // oscillation kernel followed by the fold kernel.  Returns true when the fused kernel ran.
 bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, RatesOut O, cudaStream_t st, cudaEvent_t mid,
                 int mode = kModeLlh, int det_only = -1) {
     const int n_osc = n / group;
+    if (launch_pipe(h, d_params, n, group, mode, det_only, O, st)) {
+        if (mid) CK(cudaEventRecord(mid, st));
+        return true;
+    }
     if (h->fused_ok && h->use_fused && h->gen && n_osc >= h->sm_count) {
         // inclusive / semi-inclusive / angular detectors: the same fusion with the general fold
         const RatesLaunch L = rates_launch(h, n, group, det_only);
@@ -673,6 +795,7 @@ int eval_llh_small(solarosc_handle* h, const double* params, size_t n, size_t gr
     if (!h->small_graph || h->small_n != n || h->small_group != group) {
         if (h->small_graph) { cudaGraphExecDestroy(h->small_graph); h->small_graph = nullptr; }
         cudaGraph_t g = nullptr;
+        if (n / group >= (size_t)h->sm_count) pipe_plan(h, kModeLlh, (int)group, -1);   // uploads its tables: not inside a capture
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         try {
             CK(cudaMemcpyAsync(h->d_params2[0], h->h_params_pin, n * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -771,7 +894,9 @@ int eval_llh_host(solarosc_handle* h, const double* params, size_t n, size_t gro
     return SOLAROSC_OK;
 }
 
-// Rates / per-bin evaluation of one detector; outputs copied chunk by chunk into the host arrays.
+// Rates / per-bin evaluation of one detector.  Chunks that fill the GPU run the fused pipe_kernel (the probability block
+// never goes to HBM); smaller ones osc_kernel + rates_kernel.  Two scratch slots: the kernels of chunk c + 1 are enqueued
+// before the host copies chunk c back, so copies into the caller's (usually pageable) arrays overlap the next chunk.
 int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params, size_t n, double* es_day, double* es_night,
                      double* cc_day, double* cc_night, double* bg_es, double* bg_cc) {
     REQUIRE(params, "params must not be NULL");
@@ -782,13 +907,26 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     const size_t nA = (size_t)h->n_cos[det] * nE;   // ES array entries per row (cos-scatter axis in the angular analysis)
     const size_t per = (size_t)(1 + nZ) * (nA + nC) + nE + nC;
     const int step = std::max(1, std::min(h->chunk, nA > (size_t)nE ? 128 : 1024));
-    h->ensure_scratch(per * step * sizeof(double));
+    h->ensure_scratch(2 * per * step * sizeof(double));
     h->launches = 0;
-    for (size_t b0 = 0; b0 < n; b0 += step) {
-        const int nb = (int)std::min<size_t>(step, n - b0);
-        CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
-        double* s = h->d_scratch;
+    struct Slot { RatesOut O; size_t b0; int nb; };
+    Slot sl[2];
+    auto back = [&](const Slot& s) {
+        CK(cudaEventSynchronize(h->ev_done[&s - sl]));
+        auto cp = [&](double* dst, const double* src, size_t per_pt) {
+            if (dst) CK(cudaMemcpyAsync(dst + s.b0 * per_pt, src, (size_t)s.nb * per_pt * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+        };
+        cp(es_day, s.O.es_day, nA); cp(es_night, s.O.es_night, (size_t)nZ * nA);
+        cp(cc_day, s.O.cc_day, nC); cp(cc_night, s.O.cc_night, (size_t)nZ * nC);
+        if (mode == kModeRates) { cp(bg_es, s.O.bg_es, nE); cp(bg_cc, s.O.bg_cc, nC); }
+        CK(cudaEventRecord(h->ev_out[&s - sl], h->s_out));
+    };
+    size_t c = 0;
+    for (size_t b0 = 0; b0 < n; b0 += step, ++c) {
+        const int nb = (int)std::min<size_t>(step, n - b0), slot = (int)(c & 1);
+        if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));   // chunk c - 2 has left this scratch slot
+        CK(cudaMemcpyAsync(h->d_params2[slot], params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        double* s = h->d_scratch + (size_t)slot * per * step;
         RatesOut O{};
         O.es_day = s; s += (size_t)nb * nA;
         O.es_night = s; s += (size_t)nb * nZ * nA;
@@ -796,15 +934,17 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
         O.cc_night = s; s += (size_t)nb * nZ * nC;
         O.bg_es = s; s += (size_t)nb * nE;
         O.bg_cc = s;
-        launch_rates(h, h->d_params, nb, 1, mode, det, O, h->stream);
-        CK(cudaStreamSynchronize(h->stream));
-        auto back = [&](double* dst, const double* src, size_t per_pt) {
-            if (dst) CK(cudaMemcpy(dst + b0 * per_pt, src, (size_t)nb * per_pt * sizeof(double), cudaMemcpyDeviceToHost));
-        };
-        back(es_day, O.es_day, nA); back(es_night, O.es_night, (size_t)nZ * nA);
-        back(cc_day, O.cc_day, nC); back(cc_night, O.cc_night, (size_t)nZ * nC);
-        if (mode == kModeRates) { back(bg_es, O.bg_es, nE); back(bg_cc, O.bg_cc, nC); }
+        if (!launch_pipe(h, h->d_params2[slot], nb, 1, mode, det, O, h->stream)) {
+            launch_osc(h, h->d_params2[slot], nb, 1, nullptr, h->stream);
+            launch_rates(h, h->d_params2[slot], nb, 1, mode, det, O, h->stream);
+        }
+        CK(cudaEventRecord(h->ev_done[slot], h->stream));
+        sl[slot] = Slot{O, b0, nb};
+        if (c >= 1) back(sl[slot ^ 1]);
     }
+    if (c >= 1) back(sl[(c - 1) & 1]);
+    CK(cudaStreamSynchronize(h->s_out));
+    CK(cudaStreamSynchronize(h->stream));
     return SOLAROSC_OK;
 }
 
@@ -1037,7 +1177,7 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
         const int nel_es = (1 + nZ) * nE, nel_cc = (1 + nZ) * nC, n_elem = nel_es + nel_cc + nE + nC;
         const int n_slices = 32;
         const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
-        const int step = std::max(1, std::min(h->chunk, 1024));
+        const int step = std::max(1, std::min(h->chunk, 8192));
         const size_t fixed = (size_t)nel_es + nel_cc + (size_t)(n_slices + 1) * kDerivedQ * n_elem;
         h->ensure_scratch((per * step + 5 * (size_t)step + fixed) * sizeof(double));
         double* d_lref_es = h->d_scratch;
@@ -1056,7 +1196,6 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             const int nb = (int)std::min<size_t>(step, n - b0);
             CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(d_w, weights + b0, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
             double* sp = d_rates;
             RatesOut O{};
             O.es_day = sp; sp += (size_t)nb * nE;
@@ -1065,7 +1204,10 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             O.cc_night = sp; sp += (size_t)nb * nZ * nC;
             O.bg_es = sp; sp += (size_t)nb * nE;
             O.bg_cc = sp;
-            {   // rates with row-major night arrays whatever the handle's host layout is
+            // rates with row-major night arrays whatever the handle's host layout is: the fused pipe_kernel when the chunk
+            // fills the GPU (the probability block stays on the SM), else osc_kernel + rates_kernel
+            if (!launch_pipe(h, h->d_params, nb, 1, kModeRates, det, O, h->stream, true)) {
+                launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
                 RatesLaunch L = rates_launch(h, nb, 1, det);
                 L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
                 const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
@@ -1266,6 +1408,16 @@ int solarosc_debug_read_phases(long long* out, int* n_slots, int* n_ctas) {
     cudaDeviceSynchronize();
     *n_slots = kPhaseSlots; *n_ctas = kPhaseCtas;
     return cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * kPhaseSlots * kPhaseCtas) == cudaSuccess ? 0 : 2;
+}
+#endif
+
+#ifdef SOLAROSC_PIPE_STATS
+// diagnostic builds only: read and clear the pipe_kernel cycle counters
+int solarosc_debug_read_pipe_stats(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_pipe_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return 2;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(g_pipe_stats, z, sizeof z) == cudaSuccess ? 0 : 2;
 }
 #endif
 

@@ -579,6 +579,7 @@ struct FoldTask {
     size_t b;
     int ldp, nrow, mt, kt, bte, btc;
     bool oob;
+    const double* cst_blk = nullptr;   // pipe_kernel: the additive constants of this column block only, [8]
 
     template <int NT>
     __device__ __forceinline__ void run(int col, int m0, double& part, uint32_t& fl, double& d_es, double& n_es, double& d_cc,
@@ -596,7 +597,8 @@ struct FoldTask {
         const double* m8 = (kThr ? (is_es ? D.a8_thr : D.b8_thr) : (is_es ? D.a8 : D.b8)) + ft * ldb + n0 + fg;   // B fragment of k-step 0
         const double* mh = (kThr ? (is_es ? D.ah_thr : D.bh_thr) : (is_es ? D.ah : D.bh)) + ft * ldb + n0 + fg;
         const uint32_t sc8 = smem_addr(scale + ft), sch = sc8 + 4u * kt * 8u;
-        const double c0 = v0 ? (is_es ? cst_es : cst_cc)[j0] : 0.0, c1 = v1 ? (is_es ? cst_es : cst_cc)[j0 + 1] : 0.0;
+        const double* cb = cst_blk ? cst_blk + 2 * ft : (is_es ? cst_es : cst_cc) + j0;
+        const double c0 = v0 ? cb[0] : 0.0, c1 = v1 ? cb[1] : 0.0;
         const double2* ol = is_es ? D.ol_es : D.ol_cc;                   // (m, log m) pairs, [row][nR]
         const double* obs = is_es ? D.obs_es : D.obs_cc;
         double* day = is_es ? O.es_day : O.cc_day;
