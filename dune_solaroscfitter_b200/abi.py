@@ -9,7 +9,7 @@ from typing import Any, Dict, List, Mapping, Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 8
 MAX_BG = 8
 N_FIXED_PARAMS = 8
@@ -67,7 +67,8 @@ class Tables(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("fast", C.c_int32),
-                ("earth_uncertainty", C.c_int32), ("col_major", C.c_int32), ("max_batch", C.c_int32)]
+                ("earth_uncertainty", C.c_int32), ("col_major", C.c_int32), ("max_batch", C.c_int32),
+                ("night_only", C.c_int32), ("reserved", C.c_int32)]
 
 
 _DET_F64 = ("unosc_es_nue_8b", "unosc_es_nuother_8b", "unosc_cc_8b", "unosc_es_nue_hep",
@@ -185,5 +186,6 @@ class PackedTables:
 
 
 def make_config(device: int = 0, fast: bool = True, earth_uncertainty: bool = True, col_major: bool = False,
-                max_batch: int = 0) -> Config:
-    return Config(ABI_VERSION, int(device), int(fast), int(earth_uncertainty), int(col_major), int(max_batch))
+                max_batch: int = 0, night_only: bool = False) -> Config:
+    return Config(ABI_VERSION, int(device), int(fast), int(earth_uncertainty), int(col_major), int(max_batch),
+                  int(night_only), 0)

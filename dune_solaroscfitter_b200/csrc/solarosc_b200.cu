@@ -99,6 +99,11 @@ struct solarosc_handle {
     bool fused_seg = false;
     bool rates_ok = true;
     bool fused_ok = false;
+    // binnings whose probability tile exceeds shared memory: row-chunked fold (rates_tiled_kernel)
+    int tiled_rows = 0, tiled_chunks = 0;
+    size_t tiled_smem = 0;
+    double* d_tiled_part = nullptr;
+    uint32_t* d_tiled_flags = nullptr;
     std::mutex mu;
     std::string err;
     float ms_osc = 0.f, ms_rates = 0.f;
@@ -248,7 +253,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     DevTables& T = h->T;
     T.n_etrue = t->n_etrue; T.n_e = 2 * t->n_etrue; T.n_cosz = t->n_cosz; T.n_sub = t->n_cosz_sub;
     T.n_paths = t->n_cosz * t->n_cosz_sub; T.n_layers = t->n_layers; T.n_solar = c->fast ? 0 : t->n_solar;
-    T.n_det = t->n_det; T.fast = c->fast != 0; T.earth_unc = c->earth_uncertainty != 0;
+    T.n_det = t->n_det; T.fast = c->fast != 0; T.earth_unc = c->earth_uncertainty != 0; T.night_only = c->night_only != 0;
     const int n_seg = t->seg_start[T.n_paths];
     REQUIRE(t->seg_start[0] == 0 && n_seg > 0, "seg_start must start at 0");
     T.n_seg = n_seg;
@@ -480,6 +485,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         if (s.obs_es_day && s.obs_es_night && s.obs_cc_day && s.obs_cc_night)
             upload_data(h, d, s.obs_es_day, s.obs_es_night, s.obs_cc_day, s.obs_cc_night);
     }
+    REQUIRE(!(T.night_only && h->gen), "night_only is offered for the exclusive, non-angular analysis");
     h->P = off;
     T.n_params = off;
     const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
@@ -508,6 +514,21 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaFuncSetAttribute(gen_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(gen_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
         CK(cudaFuncSetAttribute(gen_kernel<kModeAsym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+    }
+    if (!h->rates_ok) {
+        // row-chunked fold: the largest multiple of 8 rows (at most 64) whose tile fits
+        int rows = 64;
+        while (rows > 8 && tiled_smem_bytes(T.n_etrue, rows, h->max_ereco) > prop.sharedMemPerBlockOptin) rows -= 8;
+        if (tiled_smem_bytes(T.n_etrue, rows, h->max_ereco) <= prop.sharedMemPerBlockOptin) {
+            h->tiled_rows = rows;
+            h->tiled_chunks = (1 + T.n_cosz + rows - 1) / rows;
+            h->tiled_smem = tiled_smem_bytes(T.n_etrue, rows, h->max_ereco);
+            h->d_tiled_part = h->dalloc<double>((size_t)h->chunk * h->tiled_chunks);
+            h->d_tiled_flags = h->dalloc<uint32_t>((size_t)h->chunk * h->tiled_chunks);
+            CK(cudaFuncSetAttribute(rates_tiled_kernel<kModeLlh>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tiled_smem));
+            CK(cudaFuncSetAttribute(rates_tiled_kernel<kModeRates>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tiled_smem));
+            CK(cudaFuncSetAttribute(rates_tiled_kernel<kModePerbin>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tiled_smem));
+        }
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
@@ -599,6 +620,21 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
     const DevTables& T = h->T;
     const RatesLaunch L = rates_launch(h, n, group, det_only);
     const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    if (!h->rates_ok) {   // dense binnings: row-chunked fold
+        if (h->gen || h->tiled_rows == 0 || mode == kModeAsym)
+            throw ArgFail{"binning too large for the fold's shared-memory tile: this call is not available (likelihood, rates and per-bin terms of the exclusive analysis are)"};
+        const TiledLaunch TL{h->tiled_rows, h->tiled_chunks, h->d_tiled_part, h->d_tiled_flags};
+        const int grid = n * h->tiled_chunks;
+        if (mode == kModeLlh) {
+            rates_tiled_kernel<kModeLlh><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
+            tiled_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(TL, n, O.lnl, O.flags);
+            ++h->launches;
+        } else if (mode == kModeRates) rates_tiled_kernel<kModeRates><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
+        else rates_tiled_kernel<kModePerbin><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
+        CK(cudaGetLastError());
+        ++h->launches;
+        return;
+    }
     if (h->gen) {
 
         const int d = det_only >= 0 ? det_only : 0;
@@ -759,7 +795,8 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
 }
 
 void check_data(solarosc_handle* h, int det_only) {
-    if (!h->rates_ok) throw ArgFail{"binning too large for the fold's shared-memory tile: only the oscillation-stage calls are available"};
+    if (!h->rates_ok && (h->tiled_rows == 0 || h->gen))
+        throw ArgFail{"binning too large for the fold's shared-memory tile: only the oscillation-stage calls are available"};
     for (int d = 0; d < h->T.n_det; ++d)
         if ((det_only < 0 || d == det_only) && !h->has_data[d])
             throw ArgFail{"observed data not set for a detector (pass obs_* at create or call solarosc_set_data)"};
@@ -902,7 +939,7 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     REQUIRE(params, "params must not be NULL");
     REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
     if (mode == kModePerbin) check_data(h, det);
-    REQUIRE(h->rates_ok, "binning too large for the fold's shared-memory tile");
+    REQUIRE(h->rates_ok || (h->tiled_rows > 0 && !h->gen), "binning too large for the fold's shared-memory tile");
     const int nZ = h->T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
     const size_t nA = (size_t)h->n_cos[det] * nE;   // ES array entries per row (cos-scatter axis in the angular analysis)
     const size_t per = (size_t)(1 + nZ) * (nA + nC) + nE + nC;
@@ -954,6 +991,7 @@ int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, doubl
     REQUIRE(params && out_lnl && out_grad, "params, out_lnl and out_grad must not be NULL");
     REQUIRE(h->grad_ok, "binning too large for the gradient kernel's shared-memory tiles");
     REQUIRE(!h->gen, "the gradient entry serves the exclusive, non-angular analysis only");
+    REQUIRE(!h->T.night_only, "the gradient entry does not offer night_only");
     check_data(h, -1);
     const DevTables& T = h->T;
     const int n_dir = 3 + (T.earth_unc ? T.n_layers : 0), n_var = 1 + 2 * n_dir;

@@ -70,6 +70,7 @@ struct DevTables {
     int n_ltbl;                // layers some path actually crosses (1 + the largest layer id in use): the eigen table
                                // holds only these (the default binning never reaches PREM's innermost layer)
     int fast, earth_unc;
+    int night_only;            // likelihoods sum the night rows only (solarosc_config.night_only)
     const double* e_calc;      // [n_e]
     const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path
     const int2* path_se;       // [n_cosz*n_sub] (first, one-past-last) step of the paths of sorted row zr, sub-path fastest

@@ -580,13 +580,14 @@ struct FoldTask {
     int ldp, nrow, mt, kt, bte, btc;
     bool oob;
     const double* cst_blk = nullptr;   // pipe_kernel: the additive constants of this column block only, [8]
+    int row0 = 0;                      // rates_tiled_kernel: the tile holds rows row0 .. row0 + nrow - 1 of the arrays
 
     template <int NT>
     __device__ __forceinline__ void run(int col, int m0, double& part, uint32_t& fl, double& d_es, double& n_es, double& d_cc,
                                         double& n_cc) const {
         constexpr bool kThr = MODE == kModeLlh || MODE == kModeAsym;
         const int lane = threadIdx.x & 31, fg = lane >> 2, ft = lane & 3;
-        const int nZ = nrow - 1;
+        const int nZ = T.n_cosz;   // (nrow may be a row chunk: rates_tiled_kernel)
         const bool is_es = col < bte;
         const int n0 = 8 * (is_es ? col : col - bte);
         const int ldb = 8 * (is_es ? bte : btc);
@@ -631,9 +632,9 @@ struct FoldTask {
         bool vr[NT];
 #pragma unroll
         for (int c = 0; c < NT; ++c) {
-            const int row = 8 * (m0 + c) + fg;
+            const int row = 8 * (m0 + c) + fg, grow = row0 + row;
             vr[c] = m0 + c < mt && row < nrow;
-            const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
+            const double w = (grow == 0) ? 1.0 : T.wz[min(grow, T.n_cosz) - 1];
             r[c][0] = w * acc[c][0];
             r[c][1] = w * acc[c][1];
         }
@@ -641,9 +642,10 @@ struct FoldTask {
             double2 o0[NT], o1[NT];
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
-                const int row = 8 * (m0 + c) + fg;
-                o0[c] = (vr[c] && v0) ? __ldg(ol + row * nR + j0) : make_double2(0.0, 0.0);
-                o1[c] = (vr[c] && v1) ? __ldg(ol + row * nR + j0 + 1) : make_double2(0.0, 0.0);
+                const int grow = row0 + 8 * (m0 + c) + fg;
+                if (T.night_only && grow == 0) vr[c] = false;   // night-only likelihood: the day row stays out of the sum
+                o0[c] = (vr[c] && v0) ? __ldg(ol + grow * nR + j0) : make_double2(0.0, 0.0);
+                o1[c] = (vr[c] && v1) ? __ldg(ol + grow * nR + j0 + 1) : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
@@ -655,7 +657,7 @@ struct FoldTask {
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
                 const double s01 = ((vr[c] && v0) ? r[c][0] : 0.0) + ((vr[c] && v1) ? r[c][1] : 0.0);
-                const bool is_day = m0 + c == 0 && fg == 0;
+                const bool is_day = row0 + 8 * (m0 + c) + fg == 0;
                 if (is_es) { if (is_day) d_es += s01; else n_es += s01; }
                 else { if (is_day) d_cc += s01; else n_cc += s01; }
             }
@@ -663,7 +665,7 @@ struct FoldTask {
 #pragma unroll
             for (int c = 0; c < NT; ++c) {
                 if (!vr[c]) continue;
-                const int row = 8 * (m0 + c) + fg;
+                const int row = row0 + 8 * (m0 + c) + fg;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int jx = j0 + h;
@@ -848,6 +850,126 @@ rates_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ 
         }
     }
     fold_stage<MODE>(T, L, params + b * L.param_stride, b, p8s, phs, ldp, scr, O);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 + K4 + K5 for binnings whose probability tile (2 x (1 + n_cosz) x n_etrue doubles) does not fit one SM's shared
+// memory -- the dense zenith x energy grids of utils/checkOscGridConvergence.jl:36-46 (200 x 200, 1000 x 1000).  An
+// output row of the fold depends on the same row of the probabilities only, so the rows are cut into chunks of
+// TL.rows (a multiple of 8): CTA (point, chunk) stages its rows of both processes with the FULL energy axis and runs
+// the same FoldTask on them (row0 = first row of the chunk).  Likelihood partial sums land in part[point][chunk] and
+// tiled_finish_kernel adds the chunks in order (deterministic).  The oscillation stage dominates these grids by two
+// orders of magnitude, so this kernel is sized for generality, not speed.
+// ------------------------------------------------------------------------------------------
+struct TiledLaunch {
+    int rows;          // rows per chunk
+    int n_chunks;      // chunks per point
+    double* part;      // [n_points][n_chunks] likelihood partial sums
+    uint32_t* part_flags;
+};
+__host__ __device__ inline size_t tiled_smem_bytes(int n_etrue, int rows, int max_ereco) {
+    return sizeof(double) * ((size_t)2 * rows * fold_ldp(n_etrue) + fold_scratch_doubles(n_etrue, max_ereco));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+rates_tiled_kernel(const DevTables T, const RatesLaunch L, const TiledLaunch TL, const double* __restrict__ params,
+                   const double* __restrict__ osc /* [n_points/group][2][1+n_cosz][n_etrue] */, RatesOut O) {
+    extern __shared__ __align__(16) double smem[];
+    const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ, ldp = fold_ldp(nT), kt = fold_kt(nT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t b = blockIdx.x / TL.n_chunks;
+    const int rc = (int)(blockIdx.x - b * TL.n_chunks), r0 = rc * TL.rows, nr = min(TL.rows, nrow - r0);
+    double* p8s = smem;
+    double* phs = p8s + (size_t)TL.rows * ldp;
+    double* scr = phs + (size_t)TL.rows * ldp;
+    double* cst_es = scr + 8 * kt;
+    double* red = scr + fold_vec_doubles(nT, L.max_ereco);
+    uint32_t* redf = reinterpret_cast<uint32_t*>(red + kWarps);
+    const double* p = params + b * L.param_stride;
+    const double* src = osc + (b / L.group) * 2 * nrow * nT;
+    fold_zero_padding(p8s, nT, TL.rows, ldp);
+    for (int t = threadIdx.x; t < nr * nT; t += blockDim.x) {
+        const int row = t / nT, i = t - row * nT;
+        p8s[row * ldp + i] = src[(size_t)(r0 + row) * nT + i];
+        phs[row * ldp + i] = src[(size_t)(nrow + r0 + row) * nT + i];
+    }
+    bool oob = false;   // earth-norm bounds (likelihood_debug.jl:1-4)
+    if (T.earth_unc)
+        for (int k = 0; k < T.n_layers; ++k) {
+            const double x = p[SOLAROSC_N_FIXED_PARAMS + k];
+            oob |= !(x >= 0.0 && x <= 2.0);
+        }
+    RatesOut Ob = O;
+    if (rc != 0) { Ob.bg_es = nullptr; Ob.bg_cc = nullptr; }   // the background vectors are written by the first chunk
+    double total = 0.0;
+    uint32_t fl = 0;
+    for (int di = 0; di < T.n_det; ++di) {
+        if (L.det_only >= 0 && di != L.det_only) continue;
+        const DevDetector& D = T.det[di];
+        const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
+        double* cst_cc = cst_es + 8 * nte;
+        __syncthreads();
+        fold_vectors<MODE>(T, D, p, b, scr, Ob);
+        if (MODE == kModeRates || MODE == kModePerbin)   // disabled channels still produce arrays (propagation_reco.jl:12-15,119-122)
+            for (int ch = 0; ch < 2; ++ch) {
+                if (ch == 0 ? D.es_mode : D.cc_mode) continue;
+                const int nR = ch == 0 ? D.n_es : D.n_cc;
+                double* day = ch == 0 ? O.es_day : O.cc_day;
+                double* night = ch == 0 ? O.es_night : O.cc_night;
+                const long long sr = ch == 0 ? L.s_row_es : L.s_row_cc, sj = ch == 0 ? L.s_j_es : L.s_j_cc;
+                const double v = (MODE == kModePerbin && oob) ? -INFINITY : 0.0;
+                for (int o = threadIdx.x; o < nr * nR; o += blockDim.x) {
+                    const int row = r0 + o / nR, j = o % nR;
+                    if (row == 0) { if (day) day[b * nR + j] = v; }
+                    else if (night) night[b * nZ * nR + (size_t)(row - 1) * sr + (size_t)j * sj] = v;
+                }
+            }
+        __syncthreads();
+        constexpr bool kThr = MODE == kModeLlh || MODE == kModeAsym;
+        const int bte = kThr ? D.nte_thr : nte, btc = kThr ? D.ntc_thr : ntc;
+        FoldTask<MODE> F{T, L, D, O, p8s, phs, scr, cst_es, cst_cc, p[3], p[4], b, ldp, nr, (nr + 7) / 8, kt, bte, btc, oob};
+        F.row0 = r0;
+        double part = 0.0, d_es = 0.0, n_es = 0.0, d_cc = 0.0, n_cc = 0.0;
+        const int nb = bte + btc, mt = (nr + 7) / 8;
+        // work items (column block, group of kMCb row tiles) dealt round-robin over the warps
+        const int ng = (mt + kMCb - 1) / kMCb;
+        for (int it = warp; it < nb * ng; it += kWarps) {
+            const int col = it % nb, m0 = kMCb * (it / nb);
+            if (col < bte ? !D.es_mode : !D.cc_mode) continue;
+            F.template run<kMCb>(col, m0, part, fl, d_es, n_es, d_cc, n_cc);
+        }
+        total += part;
+    }
+    if (MODE != kModeLlh) return;
+    total = warp_sum(total);
+    for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+    __syncthreads();
+    if (lane == 0) { red[warp] = total; redf[warp] = fl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        uint32_t f = 0;
+        for (int w = 0; w < kWarps; ++w) { s += red[w]; f |= redf[w]; }
+        TL.part[blockIdx.x] = s;
+        TL.part_flags[blockIdx.x] = f | (oob ? 0x80000000u : 0u);
+    }
+}
+
+__global__ void tiled_finish_kernel(const TiledLaunch TL, int n_points, double* __restrict__ lnl_out, uint32_t* __restrict__ flags) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_points) return;
+    double s = 0.0;
+    uint32_t f = 0;
+    for (int k = 0; k < TL.n_chunks; ++k) { s += TL.part[(size_t)b * TL.n_chunks + k]; f |= TL.part_flags[(size_t)b * TL.n_chunks + k]; }
+    const bool oob = (f & 0x80000000u) != 0;
+    f &= 0x7fffffffu;
+    double lnl = -s;
+    if (f & SOLAROSC_FLAG_NEG_ERROR) lnl = NAN;
+    if (oob) { lnl = -INFINITY; f = SOLAROSC_FLAG_EARTH_OOB; }
+    else if (lnl != lnl) f |= (f & SOLAROSC_FLAG_NEG_ERROR) ? 0u : SOLAROSC_FLAG_NONFINITE;
+    lnl_out[b] = lnl;
+    if (flags) flags[b] = f;
 }
 
 // Persistent fused kernel: every CTA walks oscillation points g = blockIdx.x, blockIdx.x + gridDim.x, ...  Per

@@ -33,12 +33,13 @@ class SolarOscEngine:
     def __init__(self, shared: Mapping, detectors: Optional[Sequence[Mapping]] = None,
                  data: Optional[Sequence[Optional[Mapping]]] = None, *, device: int = 0, fast: bool = True,
                  earth_uncertainty: bool = True, col_major: bool = False, max_batch: int = 0,
-                 es_mode: bool = True, cc_mode: bool = True, det_names: Optional[Sequence[str]] = None):
+                 es_mode: bool = True, cc_mode: bool = True, det_names: Optional[Sequence[str]] = None,
+                 night_only: bool = False):
         self._L = _lib.load()
         if data is not None and isinstance(data, Mapping):
             data = [data]
         self.packed = abi.PackedTables(shared, detectors, data, es_mode=es_mode, cc_mode=cc_mode, col_major=col_major)
-        self.cfg = abi.make_config(device, fast, earth_uncertainty, col_major, max_batch)
+        self.cfg = abi.make_config(device, fast, earth_uncertainty, col_major, max_batch, night_only)
         st = C.c_int(0)
         self._h = self._L.solarosc_create(C.byref(self.packed.struct), C.byref(self.cfg), C.byref(st))
         if not self._h:

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define SOLAROSC_ABI_VERSION 2
+#define SOLAROSC_ABI_VERSION 3
 #define SOLAROSC_MAX_LAYERS 8   /* Earth layers (the reference's PREM has 6) */
 #define SOLAROSC_MAX_BG 8       /* background components per channel        */
 #define SOLAROSC_N_FIXED_PARAMS 8
@@ -162,6 +162,10 @@ typedef struct solarosc_config {
     int32_t earth_uncertainty;          /* earth_potential_uncertainties: 1 = earth_norm_k columns present */
     int32_t col_major;                  /* 0 = C/numpy layout, 1 = Julia layout for 2-D inputs/outputs */
     int32_t max_batch;                  /* points staged per internal chunk (0 = default 4096)        */
+    int32_t night_only;                 /* 1 = likelihoods (lnL, gradient) sum the night rows only: the day vector of
+                                           every channel stays out of the Poisson sum (BASELINE config 4, the night-only
+                                           Earth-density study); rates and per-bin outputs are unaffected         */
+    int32_t reserved;                   /* must be 0                                                  */
 } solarosc_config;
 
 typedef struct solarosc_handle solarosc_handle;

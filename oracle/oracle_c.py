@@ -47,9 +47,9 @@ class COracle:
     """The C restatement bound to one set of tables (+ data)."""
 
     def __init__(self, tables: Mapping, data: Optional[Mapping] = None, fast: bool = True,
-                 earth_uncertainty: bool = True, es_mode: bool = True, cc_mode: bool = True):
+                 earth_uncertainty: bool = True, es_mode: bool = True, cc_mode: bool = True, night_only: bool = False):
         self.packed = abi.PackedTables(tables, data=None if data is None else [data], es_mode=es_mode, cc_mode=cc_mode)
-        self.cfg = abi.make_config(fast=fast, earth_uncertainty=earth_uncertainty)
+        self.cfg = abi.make_config(fast=fast, earth_uncertainty=earth_uncertainty, night_only=night_only)
         self.P = lib().oracle_n_params(C.byref(self.packed.struct), C.byref(self.cfg))
         self.nrow = 1 + self.packed.n_cosz
 

@@ -385,10 +385,11 @@ def check_earth_norm_bounds(pv: ParamView) -> bool:
     return bool(np.all((pv.earth_norms >= 0) & (pv.earth_norms <= 2)))
 
 
-def llh_channel(rates_day, rates_night, obs_day, obs_night, idx: int, flags=None) -> float:
-    """Day vector plus every night row, bins idx:end (likelihood_builder.jl:5-20, 129-144)."""
+def llh_channel(rates_day, rates_night, obs_day, obs_night, idx: int, flags=None, night_only: bool = False) -> float:
+    """Day vector plus every night row, bins idx:end (likelihood_builder.jl:5-20, 129-144).  night_only (the
+    night-only Earth-density study of BASELINE config 4, solarosc_config.night_only) leaves the day vector out."""
     k = idx - 1
-    out = poisson_log_likelihood(rates_day[k:], obs_day[k:], flags)
+    out = 0.0 if night_only else poisson_log_likelihood(rates_day[k:], obs_day[k:], flags)
     for row, orow in zip(rates_night, obs_night):
         out += poisson_log_likelihood(row[k:], orow[k:], flags)
     return out
@@ -405,7 +406,7 @@ def llh_es_angle(rates_day, rates_night, obs_day, obs_night, idx: int, flags=Non
 
 
 def total_llh(p, t, data, fast=True, earth_uncertainty=True, use_es=True, use_cc=True,
-              precomputed_osc=None, es_mode=True, cc_mode=True) -> float:
+              precomputed_osc=None, es_mode=True, cc_mode=True, night_only=False) -> float:
     """likelihood_main.jl:8-35 + likelihood_builder.jl:216-259 for one detector: use_ES = ES_mode,
     use_CC = CC_mode && (!inclusive || semi_inclusive), llh_ES_angle when angular."""
     pv = view(p, t)
@@ -418,9 +419,9 @@ def total_llh(p, t, data, fast=True, earth_uncertainty=True, use_es=True, use_cc
     if use_es and _flag(t, "angular"):
         llh += llh_es_angle(r["ES_day"], r["ES_night"], data["ES_day"], data["ES_night"], int(t["index_es"]))
     elif use_es:
-        llh += llh_channel(r["ES_day"], r["ES_night"], data["ES_day"], data["ES_night"], int(t["index_es"]))
+        llh += llh_channel(r["ES_day"], r["ES_night"], data["ES_day"], data["ES_night"], int(t["index_es"]), night_only=night_only)
     if use_cc:
-        llh += llh_channel(r["CC_day"], r["CC_night"], data["CC_day"], data["CC_night"], int(t["index_cc"]))
+        llh += llh_channel(r["CC_day"], r["CC_night"], data["CC_day"], data["CC_night"], int(t["index_cc"]), night_only=night_only)
     return llh
 
 

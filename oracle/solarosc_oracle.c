@@ -375,9 +375,11 @@ double oracle_poisson(const double *e_in, const double *m_in, size_t n, uint32_t
     return -llh;
 }
 
-static double llh_channel(const double *r, const double *od, const double *on, int nrow, int nR, int idx, uint32_t *fl) {
+static double llh_channel(const double *r, const double *od, const double *on, int nrow, int nR, int idx, uint32_t *fl,
+                          int night_only) {
     int k = idx - 1;
-    double s = oracle_poisson(r + k, od + k, nR - k, fl); /* likelihood_builder.jl:5-20,129-144 */
+    /* likelihood_builder.jl:5-20,129-144; night_only (solarosc_config, BASELINE config 4) drops the day vector */
+    double s = night_only ? 0.0 : oracle_poisson(r + k, od + k, nR - k, fl);
     double night = 0;
     for (int row = 1; row < nrow; ++row)
         night += oracle_poisson(r + (size_t)row * nR + k, on + (size_t)(row - 1) * nR + k, nR - k, fl);
@@ -407,8 +409,8 @@ static double llh_point(const solarosc_tables *t, const solarosc_config *c, cons
         double *be = malloc(sizeof(double) * d->n_ereco_es), *bc = malloc(sizeof(double) * d->n_ereco_cc);
         rates_det(t, c, det, p, osc, es, cc, be, bc);
         double l = 0.0;
-        if (d->es_mode) l += llh_channel(es, d->obs_es_day, d->obs_es_night, nrow, d->n_ereco_es, d->index_es, &fl);
-        if (d->cc_mode) l += llh_channel(cc, d->obs_cc_day, d->obs_cc_night, nrow, d->n_ereco_cc, d->index_cc, &fl);
+        if (d->es_mode) l += llh_channel(es, d->obs_es_day, d->obs_es_night, nrow, d->n_ereco_es, d->index_es, &fl, c->night_only);
+        if (d->cc_mode) l += llh_channel(cc, d->obs_cc_day, d->obs_cc_night, nrow, d->n_ereco_cc, d->index_cc, &fl, c->night_only);
         tot += l;
         free(es); free(cc); free(be); free(bc);
     }

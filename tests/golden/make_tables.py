@@ -129,32 +129,15 @@ def build(ref: str, n_cosz: int = 50, n_cosz_fine: int = 20, cosz_fine_edge: flo
     )
 
 
-def build_osc_only(ref: str, n_cosz: int, n_etrue: int, n_cosz_fine: int = 0):
-    """Shared oscillation tables only (dense zenith x energy grids of SURVEY.md section 8(d) C4;
-    utils/checkOscGridConvergence.jl:44,122-145 sweeps 1000 x 1000).  Detector tables are stubs."""
-    inp = os.path.join(ref, "inputs")
-    etrue = tb.BinSpec(n_etrue, 1e-3, 21e-3)
-    model = tb.load_earth_model(os.path.join(inp, "EARTH_MODEL_PREM_DENSE.dat"))
-    earth = tb.Linear1D(model["radius"], model["potential"], mode="throw")
-    ex_x, ex_y = tb.load_exposure(os.path.join(inp, "solarExposure.csv"))
-    grid = tb.build_cosz_grid(model, n_cosz, ex_x, n_fine=n_cosz_fine)
-    paths, lookup = tb.build_earth_tables(earth, grid.cosz_calc, 6)
-    seg_start, seg_layer, seg_length = tb.pack_paths(paths)
-    ssm = tb.solar_model(hdf5_min.load(os.path.join(inp, "AGSS09_high_z.jld2")))
-    _, e_fine = tb.calculate_bins(tb.BinSpec(2 * n_etrue, etrue.min, etrue.max))
-    z1 = np.zeros(n_etrue)
-    return dict(
-        n_cosz_sub=np.int32(grid.n_sub), cosz_calc=grid.cosz_calc, e_calc=e_fine,
-        seg_start=seg_start, seg_layer=seg_layer, seg_length=seg_length, earth_lookup=lookup,
-        exposure_weights=tb.exposure_weights(ex_x, ex_y, grid.edges),
-        avg_ne_8b=np.float64(ssm["avgNeBoron"]), avg_ne_hep=np.float64(ssm["avgNeHep"]),
-        unosc_es_nue_8b=z1, unosc_es_nuother_8b=z1, unosc_cc_8b=z1, unosc_es_nue_hep=z1, unosc_es_nuother_hep=z1,
-        unosc_cc_hep=z1, log_e_norm=z1, resp_es_nue=np.zeros((n_etrue, 2)), resp_es_nuother=np.zeros((n_etrue, 2)),
-        resp_cc=np.zeros((n_etrue, 2)), eff_es_nue=np.zeros(2), eff_es_nuother=np.zeros(2), eff_cc=np.zeros(2),
-        raw_bg_es=np.zeros((1, 2)), bg_es_sides=np.zeros(1, dtype=np.int32), bg_es_par=np.zeros(1, dtype=np.int32),
-        raw_bg_cc=np.zeros((1, 2)), bg_cc_par=np.zeros(1, dtype=np.int32), index_es=np.int32(1), index_cc=np.int32(1),
-        truth=np.array([0.307, 0.0224, 6e-5, 5.25e6, 8250.0, 1.0, 0.0, 0.0] + [1.0] * 6),
-    )
+def build_dense(ref: str, n_cosz: int, n_etrue: int):
+    """The measurement configuration on a dense zenith x energy grid (SURVEY.md section 8(d) C4;
+    utils/checkOscGridConvergence.jl:36-46,122-145 sweeps 1000 cos z x 1000 E): the same inputs, detector tables
+    included -- the CC response rebinned from the shipped MC to n_etrue true-energy bins, the unoscillated spectra
+    integrated on them -- without the per-event bin indices."""
+    t = build(ref, n_cosz=n_cosz, n_cosz_fine=0, n_etrue=n_etrue)
+    for k in ("cc_mc_true_bin", "cc_mc_reco_bin", "cc_mc_in_range", "solar_ne", "solar_prod_8b", "solar_prod_hep"):
+        t.pop(k)
+    return t
 
 
 def main():
@@ -171,8 +154,8 @@ def main():
     print("earth_lookup", t["earth_lookup"])
     print("sum w_z", t["exposure_weights"].sum())
     here = os.path.dirname(a.out)
-    for name, nz, nt in (("tables_dense200_osc.npz", 200, 100), ("tables_dense1000_osc.npz", 1000, 500)):
-        d = build_osc_only(a.ref, nz, nt)
+    for name, nz, nt in (("tables_dense200.npz", 200, 100), ("tables_dense1000.npz", 1000, 500)):
+        d = build_dense(a.ref, nz, nt)
         np.savez_compressed(os.path.join(here, name), **d)
         per = np.diff(d["seg_start"])
         print(f"{name}: paths={len(per)} n_sub={d['n_cosz_sub']} segments={int(per.sum())} max={per.max()} energies={len(d['e_calc'])}")

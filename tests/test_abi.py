@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.solarosc_abi_version() == abi.ABI_VERSION == 2
+    assert lib.solarosc_abi_version() == abi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header(tmp_path):

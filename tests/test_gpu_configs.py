@@ -62,30 +62,70 @@ def _earth_draws(t, n, seed):
     return p
 
 
+def _oracle_data(t):
+    """Observed data of a dense configuration: the C oracle's rates at the truth (an input table like any other)."""
+    from oracle import oracle_c
+    r = oracle_c.COracle(t, None).eval_rates(np.asarray(t["truth"], dtype=float))
+    return {k: r[k][0] for k in ("ES_day", "ES_night", "CC_day", "CC_night")}
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
 def test_c4_dense_200x200_matches_oracle():
+    """200 zenith x 200 energies with the full detector tables: oscillation stage, rates and the likelihood
+    (ES+CC, CC alone, night-only CC) through the row-chunked fold, against the oracle."""
     from dune_solaroscfitter_b200.engine import SolarOscEngine
     from oracle import oracle_c
-    t = _dense("tables_dense200_osc.npz")
+    t = _dense("tables_dense200.npz")
     p = _earth_draws(t, 3, 5)
     ref_osc, ref_p1e = oracle_c.COracle(t, None).eval_oscprobs(p, want_p1e=True)
-    with SolarOscEngine(t) as e:
+    data = _oracle_data(t)
+    with SolarOscEngine(t, data=data) as e:
         p1e = e.eval_p1e(p)
         osc = e.eval_oscprobs(p)
+        lnl, fl = e.eval_llh(p, return_flags=True)
+        rates = e.eval_rates(p)
+        perbin = e.eval_perbin(p[:1])
+        big = _earth_draws(t, 300, 6)                                  # more points than SMs
+        lnl_big = e.eval_llh(big)
     assert p1e.shape == (3, 200, 200)
     assert np.max(np.abs(p1e - ref_p1e)) < 5e-12
     assert np.max(np.abs(osc["nue_8B_night"] - ref_osc[:, 0, 1:])) < 5e-12
     assert np.max(np.abs(osc["nue_hep_day"] - ref_osc[:, 1, 0])) < 1e-14
+    orc = oracle_c.COracle(t, data)
+    ref_lnl, ref_fl = orc.eval_llh(p)
+    ref_rates = orc.eval_rates(p)
+    assert np.array_equal(fl, ref_fl)
+    assert np.max(np.abs(2 * lnl - 2 * ref_lnl)) < 1e-6                 # BASELINE.json tolerance
+    for k in ("ES_day", "ES_night", "CC_day", "CC_night"):
+        assert rates[k].shape == ref_rates[k].shape
+        assert _rel(rates[k], ref_rates[k]) < 1e-9, k
+    assert perbin["CC_night"].shape == (1, 200, 30) and np.all(perbin["CC_night"][:, :, -1] == 0)
+    assert np.max(np.abs(2 * lnl_big - 2 * orc.eval_llh(big)[0])) < 1e-6
+    # night-only CC (BASELINE config 4): ES off, the day vector out of the sum
+    ref_n, _ = oracle_c.COracle(t, data, es_mode=False, night_only=True).eval_llh(p)
+    with SolarOscEngine(t, data=data, es_mode=False, night_only=True) as e:
+        got_n = e.eval_llh(p)
+    assert np.max(np.abs(2 * got_n - 2 * ref_n)) < 1e-6
+    assert np.max(np.abs(ref_n - ref_lnl)) > 1e-3                       # (it is a different number)
 
 
 def test_c4_dense_1000x1000_sweep():
-    """The 1000 cos z x 1000 E grid of utils/checkOscGridConvergence.jl: too large for the fold's
-    shared-memory tile, so only the oscillation-stage calls are offered -- and they match the oracle."""
-    from dune_solaroscfitter_b200.engine import SolarOscEngine, SolarOscError
+    """The 1000 cos z x 1000 E grid of utils/checkOscGridConvergence.jl:36-46: the probability tile (8 MB per point)
+    is 35 x one SM's shared memory, the fold runs row-chunked from HBM -- oscillation stage, CC night rates and the
+    night-only CC likelihood against the oracle."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
     from oracle import oracle_c
-    t = _dense("tables_dense1000_osc.npz")
+    t = _dense("tables_dense1000.npz")
     p = _earth_draws(t, 2, 9)
     ref_osc, ref_p1e = oracle_c.COracle(t, None).eval_oscprobs(p[:1], want_p1e=True)
-    with SolarOscEngine(t) as e:
+    data = _oracle_data(t)
+    orc = oracle_c.COracle(t, data, es_mode=False, night_only=True)
+    ref_lnl, ref_fl = orc.eval_llh(p)
+    ref_rates = orc.eval_rates(p[:1])
+    with SolarOscEngine(t, data=data, es_mode=False, night_only=True) as e:
         p1e = e.eval_p1e(p)
         assert p1e.shape == (2, 1000, 1000)
         assert np.max(np.abs(p1e[0] - ref_p1e[0])) < 5e-12
@@ -93,24 +133,39 @@ def test_c4_dense_1000x1000_sweep():
         assert np.max(np.abs(osc["nue_8B_night"][0] - ref_osc[0, 0, 1:])) < 5e-12
         v = p[1].copy(); v[8:14] = 0.0                                  # vacuum: size-independent property
         assert np.max(np.abs(e.eval_p1e(v) - (1 - v[0]) * (1 - v[1]))) < 1e-14
-        with pytest.raises(SolarOscError):
-            e.eval_llh(p)
+        lnl, fl = e.eval_llh(p, return_flags=True)
+        rates = e.eval_rates(p[:1])
+        oob = p.copy(); oob[1, 9] = 2.5
+        lo, flo = e.eval_llh(oob, return_flags=True)
+    assert np.array_equal(fl, ref_fl) and np.max(np.abs(2 * lnl - 2 * ref_lnl)) < 1e-6
+    assert _rel(rates["CC_night"], ref_rates["CC_night"]) < 1e-9 and _rel(rates["CC_day"], ref_rates["CC_day"]) < 1e-9
+    assert np.all(rates["ES_night"] == 0)                               # propagation_reco.jl:12-15
+    assert lo[0] == lnl[0] and lo[1] == -np.inf and flo[1] == 1         # earth-norm bound (likelihood_debug.jl:1-4)
 
 
 def test_c4_night_only_cc_default_grid(tables, draw):
-    """Night-only CC likelihood with earth-norm draws, B = 4096: ES off, day data zero-weighted by comparing
-    against the oracle configured the same way."""
+    """Night-only CC likelihood with earth-norm draws, B = 4096, on the default grid: ES off (CC day row still in the
+    sum), then truly night-only (solarosc_config.night_only: the day vector out of the sum), each against the oracle
+    configured the same way; 4096 points take the fused kernel, 16 the small-batch kernels."""
     from dune_solaroscfitter_b200.engine import SolarOscEngine
     from oracle import oracle_c, oracle_np
     data = oracle_np.asimov_data(tables)
     p = np.tile(np.asarray(tables["truth"], dtype=float), (4096, 1))
     p[:, 8:14] = np.clip(np.random.default_rng(3).normal(1.0, 0.12, (4096, 6)), 0.0, 2.0)
+    p[:64, 0] = 0.33                                                   # off the Asimov point: the day term is not zero
     ref, _ = oracle_c.COracle(tables, data, es_mode=False).eval_llh(p)
     with SolarOscEngine(tables, data=data, es_mode=False) as e:
         got = e.eval_llh(p)
         r = e.eval_rates(p[:2])
     assert np.max(np.abs(2 * got - 2 * ref)) < 1e-6
     assert np.all(r["ES_day"] == 0) and np.all(r["ES_night"] == 0)     # propagation_reco.jl:12-15
+    ref_n, _ = oracle_c.COracle(tables, data, es_mode=False, night_only=True).eval_llh(p)
+    with SolarOscEngine(tables, data=data, es_mode=False, night_only=True) as e:
+        got_n, got_small, got_grp = e.eval_llh(p), e.eval_llh(p[:16]), e.eval_llh(p, group=1)
+        r_n = e.eval_rates(p[:2])
+    assert np.max(np.abs(2 * got_n - 2 * ref_n)) < 1e-6 and np.max(np.abs(2 * got_small - 2 * ref_n[:16])) < 1e-6
+    assert np.max(np.abs(ref_n - ref)) > 1e-3
+    assert np.array_equal(r_n["CC_day"], r["CC_day"])                    # rates do not change, only the sum
 
 
 # ---- C5: derived quantities over a stored chain ---------------------------------------------------------------------------
