@@ -14,7 +14,7 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_pipe.cuh", "solarosc_grad.cuh", "solarosc_general.cuh", "solarosc_setup.cuh", "solarosc_batcher.hpp")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_pipe.cuh", "solarosc_grad.cuh", "solarosc_adjoint.cuh", "solarosc_adjoint_math.cuh", "solarosc_general.cuh", "solarosc_setup.cuh", "solarosc_batcher.hpp")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (

@@ -15,7 +15,7 @@
 #include <thread>
 #include <vector>
 
-#include "solarosc_grad.cuh"
+#include "solarosc_adjoint.cuh"
 #include "solarosc_pipe.cuh"
 #include "solarosc_general.cuh"
 #include "solarosc_setup.cuh"
@@ -88,9 +88,10 @@ struct solarosc_handle {
     bool small_fused = false;
     uint32_t* h_flags2[2]{};
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
-    double* d_gradws = nullptr;  // gradient path: probabilities of each point and its shifted copies, then the gradients
+    double* d_gradws = nullptr;  // gradient path, two slots: probabilities, d lnL / d P, gradient rows
     size_t gradws_bytes = 0;
-    size_t grad_smem = 0;
+    size_t grad_smem = 0, adj_smem = 0;
+    double* h_grad_pin[2]{};     // pinned staging of the gradient rows of one chunk
     bool grad_ok = false;
     size_t scratch_bytes = 0;
     size_t osc_smem_limit = 200 * 1024;
@@ -532,8 +533,12 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     }
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
-    h->grad_ok = h->grad_smem <= prop.sharedMemPerBlockOptin;
-    if (h->grad_ok) CK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_smem));
+    h->adj_smem = sizeof(double) * (adj_smem_doubles(T.n_ltbl, T.n_e, seg_smem_doubles(T.n_seg, T.n_paths, T.n_cosz)) + 2);
+    h->grad_ok = h->grad_smem <= prop.sharedMemPerBlockOptin && h->adj_smem <= prop.sharedMemPerBlockOptin;
+    if (h->grad_ok) {
+        CK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_smem));
+        CK(cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->adj_smem));
+    }
     // Fused kernel: the energy axis is walked in chunks of fused_cb coarse bins, the smallest eigen table that
     // still gives the propagation loop whole passes of work (n_cosz * cb items over kThreads threads), so that
     // SOLAROSC_LLH_MINBLOCKS CTAs fit the SM's shared memory.  SOLAROSC_LLH_CHUNKS overrides the chunk count.
@@ -581,8 +586,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
 
 // ---- launches ------------------------------------------------------------------------------------
 void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point_step, double* d_p1e, cudaStream_t st,
-                int n_var = 1, double* d_out = nullptr) {
-    n_osc *= n_var;   // every variant is an output slot of its own
+                double* d_out = nullptr) {
     const DevTables& T = h->T;
     // coarse bins per CTA: the whole spectrum when the batch alone fills the GPU, otherwise split the
     // energy axis so that about two CTAs per SM exist; never more than shared memory holds
@@ -596,7 +600,7 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     size_t sm = osc_smem_bytes(T.n_ltbl, cb);
     const bool seg = sm + h->seg_bytes <= std::min<size_t>(h->osc_smem_limit, 110 * 1024);
     if (seg) sm += h->seg_bytes;
-    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0, n_var};
+    OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0};
     osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, d_out ? d_out : h->d_osc, d_p1e);
     CK(cudaGetLastError());
     ++h->launches;
@@ -985,47 +989,64 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
     return SOLAROSC_OK;
 }
 
-// lnL and its gradient.  Per chunk: osc_kernel evaluates every point and its 2 n_dir shifted copies into the
-// workspace, grad_kernel folds, differentiates and reduces; lnL, gradient rows and flags come back together.
+// lnL and its gradient.  Per chunk: osc_kernel writes the probabilities, grad_kernel folds, differentiates the Poisson sum and
+// folds back (flux, cross-section and background columns; d lnL / d P to the workspace), adjoint_kernel carries d lnL / d P
+// through the oscillation stage exactly (mixing, dm2_21 and earth-norm columns).  Two workspace slots: the kernels of chunk
+// c + 1 are enqueued before the host collects chunk c.
 int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad, uint32_t* flags) {
     REQUIRE(params && out_lnl && out_grad, "params, out_lnl and out_grad must not be NULL");
-    REQUIRE(h->grad_ok, "binning too large for the gradient kernel's shared-memory tiles");
+    REQUIRE(h->grad_ok, "binning too large for the gradient kernels' shared-memory tiles");
     REQUIRE(!h->gen, "the gradient entry serves the exclusive, non-angular analysis only");
     REQUIRE(!h->T.night_only, "the gradient entry does not offer night_only");
     check_data(h, -1);
     const DevTables& T = h->T;
-    const int n_dir = 3 + (T.earth_unc ? T.n_layers : 0), n_var = 1 + 2 * n_dir;
     const size_t osc_pt = (size_t)2 * (1 + T.n_cosz) * T.n_etrue;
-    const int step = std::max(1, std::min(h->chunk, 1024));
-    const size_t need = ((size_t)step * n_var * osc_pt + (size_t)step * h->P) * sizeof(double);
+    const int step = std::max(1, std::min(h->chunk, 4096));
+    const size_t slot_doubles = (size_t)step * (2 * osc_pt + h->P);
+    const size_t need = 2 * slot_doubles * sizeof(double);
     if (need > h->gradws_bytes) {
         if (h->d_gradws) CK(cudaFree(h->d_gradws));
         h->d_gradws = nullptr; h->gradws_bytes = 0;
         CK(cudaMalloc(reinterpret_cast<void**>(&h->d_gradws), need));
         h->gradws_bytes = need;
     }
-    double* d_var = h->d_gradws;
-    double* d_grad = d_var + (size_t)step * n_var * osc_pt;
-    std::vector<uint32_t> fl(step);
+    if (!h->h_grad_pin[0])
+        for (int i = 0; i < 2; ++i) CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_grad_pin[i]), (size_t)std::min(h->chunk, 4096) * h->P * sizeof(double)));
     bool neg = false;
     h->launches = 0;
-    for (size_t b0 = 0; b0 < n; b0 += step) {
-        const int nb = (int)std::min<size_t>(step, n - b0);
-        CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_osc(h, h->d_params, nb, 1, nullptr, h->stream, n_var, d_var);
-        GradLaunch G{nb, h->P, h->max_ereco, n_dir, n_var};
-        grad_kernel<<<nb, kThreads, h->grad_smem, h->stream>>>(T, G, h->d_params, d_var, h->d_lnl2[0], d_grad, h->d_flags2[0]);
+    struct Slot { size_t b0; int nb; };
+    Slot sl[2];
+    auto collect = [&](int slot) {
+        const Slot& s = sl[slot];
+        CK(cudaEventSynchronize(h->ev_out[slot]));
+        std::memcpy(out_lnl + s.b0, h->h_lnl2[slot], (size_t)s.nb * sizeof(double));
+        std::memcpy(out_grad + s.b0 * h->P, h->h_grad_pin[slot], (size_t)s.nb * h->P * sizeof(double));
+        const uint32_t* f = h->h_flags2[slot];
+        for (int i = 0; i < s.nb; ++i) neg |= (f[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+        if (flags) std::memcpy(flags + s.b0, f, (size_t)s.nb * sizeof(uint32_t));
+    };
+    size_t c = 0;
+    for (size_t b0 = 0; b0 < n; b0 += step, ++c) {
+        const int nb = (int)std::min<size_t>(step, n - b0), slot = (int)(c & 1);
+        if (c >= 2) collect(slot);   // chunk c - 2 has left this slot's pinned staging (and its device buffers)
+        double* d_osc = h->d_gradws + (size_t)slot * slot_doubles;
+        double* d_pbar = d_osc + (size_t)step * osc_pt;
+        double* d_grad = d_pbar + (size_t)step * osc_pt;
+        CK(cudaMemcpyAsync(h->d_params2[slot], params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_osc(h, h->d_params2[slot], nb, 1, nullptr, h->stream, d_osc);
+        GradLaunch G{nb, h->P, h->max_ereco};
+        grad_kernel<<<nb, kThreads, h->grad_smem, h->stream>>>(T, G, h->d_params2[slot], d_osc, d_pbar, h->d_lnl2[slot], d_grad, h->d_flags2[slot]);
+        AdjLaunch A{nb, h->P};
+        adjoint_kernel<<<nb, kThreads, h->adj_smem, h->stream>>>(T, A, h->d_params2[slot], d_pbar, d_grad, h->d_flags2[slot]);
         CK(cudaGetLastError());
-        ++h->launches;
-        CK(cudaMemcpyAsync(out_lnl + b0, h->d_lnl2[0], nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(out_grad + b0 * h->P, d_grad, (size_t)nb * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(fl.data(), h->d_flags2[0], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        for (int i = 0; i < nb; ++i) {
-            neg |= (fl[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
-            if (flags) flags[b0 + i] = fl[i];
-        }
+        h->launches += 2;
+        CK(cudaMemcpyAsync(h->h_lnl2[slot], h->d_lnl2[slot], nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_grad_pin[slot], d_grad, (size_t)nb * h->P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_flags2[slot], h->d_flags2[slot], nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_out[slot], h->stream));
+        sl[slot] = Slot{b0, nb};
     }
+    for (size_t k = c >= 2 ? c - 2 : 0; k < c; ++k) collect((int)(k & 1));
     if (neg) {
         h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
         return SOLAROSC_ERR_NEGATIVE_RATE;
@@ -1083,6 +1104,8 @@ void solarosc_destroy(solarosc_handle* h) {
     if (h->d_gradws) cudaFree(h->d_gradws);
     if (h->small_graph) cudaGraphExecDestroy(h->small_graph);
     if (h->h_params_pin) cudaFreeHost(h->h_params_pin);
+    for (int i = 0; i < 2; ++i)
+        if (h->h_grad_pin[i]) cudaFreeHost(h->h_grad_pin[i]);
     for (int i = 0; i < 2; ++i) {
         if (h->h_lnl2[i]) cudaFreeHost(h->h_lnl2[i]);
         if (h->h_flags2[i]) cudaFreeHost(h->h_flags2[i]);

@@ -12,22 +12,20 @@
 //   diagonal in x, so their derivatives are reductions of G against pieces the forward fold already holds.
 //   The BACKWARD fold  Pbar[row][i] = d lnL / d P[row][i] = F (G_ES A^T + diag(s) G_CC B^T)  runs on the FP64
 //   tensor pipe like the forward one.  The oscillation parameters (sin2_th12, sin2_th13, dm2_21, earth_norm_k)
-//   enter only through the probabilities: d lnL / d theta = <Pbar, dP/d theta>, with dP/d theta from central
-//   differences of the oscillation stage (osc_kernel evaluates the 2 n_dir shifted points next to the base
-//   point in the same launch).  Steps: 1e-4 on the mixing angles and earth norms, 1e-6 relative on dm2_21;
-//   the probabilities carry ~1e-11 of rounding noise, so these directions are good to ~1e-6 relative, the
-//   others to rounding.  That is ample for HMC, whose accept step does not depend on gradient accuracy.
+//   enter only through the probabilities: d lnL / d theta = <Pbar, dP/d theta>.  grad_kernel writes Pbar and
+//   adjoint_kernel (solarosc_adjoint.cuh) contracts it with the exact derivatives of the oscillation stage in one
+//   backward sweep per (path, energy) -- every column of the gradient is exact to rounding, like the reference's
+//   dual numbers.
 #pragma once
 #include "solarosc_kernels.cuh"
 
 namespace solarosc {
 
-constexpr int kMaxDir = 3 + SOLAROSC_MAX_LAYERS;   // oscillation-stage directions
-constexpr int kGradShared = 6 + kMaxDir;           // lnL, F8, Fh, xsec norm/tilt/curv, directions
+constexpr int kGradShared = 6;                     // lnL, F8, Fh, xsec norm/tilt/curv
 constexpr int kGradBg = 1 + SOLAROSC_MAX_BG;       // ES norm_1, CC norms
 
 struct GradLaunch {
-    int n_points, param_stride, max_ereco, n_dir, n_var;
+    int n_points, param_stride, max_ereco;
 };
 
 // leading dimension of a shared-memory A operand of the given K extent: multiple of 4, congruent 12 mod 16
@@ -96,11 +94,13 @@ __device__ __forceinline__ void block_reduce(const double (&v)[N], double* red /
     __syncthreads();
 }
 
-// One CTA per parameter point.  osc_var holds the oscillation probabilities of the point and of its
-// 2 n_dir shifted copies, [n_points][n_var][2 proc][1 + n_cosz][n_etrue], as osc_kernel writes them.
+// One CTA per parameter point.  osc holds the oscillation probabilities [n_points][2 proc][1 + n_cosz][n_etrue] as
+// osc_kernel writes them; pbar_out receives d lnL / d P in the same layout (adjoint_kernel's input).  The gradient row
+// is zeroed, then the flux, cross-section and background columns are written; the oscillation columns stay zero here.
 __global__ void __launch_bounds__(kThreads, 1)
-grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ params, const double* __restrict__ osc_var,
-            double* __restrict__ out_lnl, double* __restrict__ out_grad /* [n_points][n_params] */, uint32_t* __restrict__ out_flags) {
+grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ params, const double* __restrict__ osc,
+            double* __restrict__ pbar_out, double* __restrict__ out_lnl, double* __restrict__ out_grad /* [n_points][n_params] */,
+            uint32_t* __restrict__ out_flags) {
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t redf[kWarps];
     const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ, ldp = fold_ldp(nT), rows = fold_rows(nrow);
@@ -128,7 +128,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
     const size_t b = blockIdx.x;
     const double* p = params + b * L.param_stride;
     const size_t var_stride = (size_t)2 * nrow * nT;
-    const double* base = osc_var + b * L.n_var * var_stride;
+    const double* base = osc + b * var_stride;
     const int P = T.n_params;
     const double f8 = p[3], fh = p[4];
 
@@ -371,19 +371,13 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
             for (int k = 0; k < D.n_norm_cc; ++k) out_grad[b * P + D.param_off + D.n_norm_es + k] = tot[kGradShared + 1 + k];
         }
     }
-    // ---- oscillation directions: <Pbar, (P+ - P-)> / (2 step) -----------------------------------------------------
+    // ---- d lnL / d P to HBM: adjoint_kernel carries it through the oscillation stage ------------------------------------
     __syncthreads();
     {
-        const int n_el = 2 * nrow * nT;
-        for (int e = threadIdx.x; e < n_el; e += blockDim.x) {
+        double* dst = pbar_out + b * var_stride;
+        for (int e = threadIdx.x; e < 2 * nrow * nT; e += blockDim.x) {
             const int proc = e / (nrow * nT), rem = e - proc * nrow * nT, row = rem / nT, i = rem - row * nT;
-            const double qb = (proc ? qhs : q8s)[row * ldp + i];
-#pragma unroll
-            for (int d = 0; d < kMaxDir; ++d)
-                if (d < L.n_dir) {
-                    const double pp = base[(size_t)(1 + 2 * d) * var_stride + e], pm = base[(size_t)(2 + 2 * d) * var_stride + e];
-                    sh[6 + d] = fma(qb, pp - pm, sh[6 + d]);
-                }
+            dst[e] = (proc ? qhs : q8s)[row * ldp + i];
         }
     }
     for (int o = 16; o > 0; o >>= 1) fl |= __shfl_xor_sync(0xffffffffu, fl, o);
@@ -404,14 +398,8 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
         for (int k = threadIdx.x; k < P; k += blockDim.x) out_grad[b * P + k] = 0.0;
         return;
     }
-    if (threadIdx.x >= 1 && threadIdx.x < kGradShared) {
-        const int k = threadIdx.x;
-        if (k <= 5) out_grad[b * P + k + 2] = tot[k];   // fluxes -> columns 3, 4; cross-section norm / tilt / curvature -> 5..7
-        else if (k - 6 < L.n_dir) {
-            const int col = grad_dir_col(k - 6);
-            out_grad[b * P + col] = tot[k] / (2.0 * grad_step(col, p));
-        }
-    }
+    if (threadIdx.x >= 1 && threadIdx.x < kGradShared)
+        out_grad[b * P + threadIdx.x + 2] = tot[threadIdx.x];   // fluxes -> columns 3, 4; cross-section norm / tilt / curvature -> 5..7
 }
 
 }  // namespace solarosc

@@ -48,7 +48,6 @@ struct OscLaunch {
     int param_stride; // doubles between consecutive points' parameter rows
     int point_step;   // parameter row of oscillation point g is g*point_step (grouped evaluation)
     int seg_smem;     // path tables staged in shared memory behind the eigen table
-    int n_var;        // 1, or 1 + 2*n_dir: every point is followed by its +/- finite-difference variants
 };
 
 // Phase timestamps of a window of CTAs (diagnostic builds only: -DSOLAROSC_PHASE_TIMING, read back with
@@ -126,13 +125,6 @@ __host__ __device__ inline size_t llh_smem_bytes(int n_layers, int cb, int n_etr
                              seg_doubles + tail);
 }
 
-// Oscillation-stage directions of the gradient path: sin2_th12, sin2_th13, dm2_21, then earth_norm_k.
-__host__ __device__ inline int grad_dir_col(int d) { return d < 3 ? d : SOLAROSC_N_FIXED_PARAMS + (d - 3); }
-// Central-difference half-step of column col: 1e-6 relative on dm2_21, 1e-4 absolute on the mixing angles and
-// earth norms.  The probabilities are smooth on these scales and carry ~1e-11 of rounding noise, so truncation and
-// noise both stay near 1e-7 of the derivative (derivation in solarosc_grad.cuh).
-__host__ __device__ inline double grad_step(int col, const double* p) { return col == 2 ? 1e-6 * p[2] : 1e-4; }
-
 // ------------------------------------------------------------------------------------------
 // K1 + K2.  `sink.put(row, i, p8, ph)` receives the block-averaged nu_e survival probabilities of
 // coarse energy bin i for row 0 (day) and rows 1 + z (night zenith bin z).  Ends without a barrier.
@@ -206,31 +198,21 @@ __device__ __forceinline__ double sqrt01(double x) { return x > 0.0 ? sqrt_pos(x
 
 template <bool SEG_SMEM, class Sink>
 __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G, const double* __restrict__ p, int i0, int cb,
-                                          int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink,
-                                          int vcol = -1, double vdelta = 0.0) {
-    // (vcol, vdelta): parameter column shifted by vdelta -- the finite-difference variants of the gradient path
+                                          int cbs, double* tbl, double* msw, double* __restrict__ p1e_out, const Sink sink) {
     const int ne = 2 * cb;   // fine energies handled here
     const int nl = T.n_ltbl;
     // mixing parameters (reference propagation_osc.jl:30-36: theta = asin(sqrt(clamp(sin2, 0, 1))))
     // clamp(x, 0, 1) that lets a NaN through like Julia's does (fmin / fmax would turn it into 0)
     auto clamp01 = [](double x) { return x != x ? x : fmin(fmax(x, 0.0), 1.0); };
-    const double s12sq = clamp01(p[0] + (vcol == 0 ? vdelta : 0.0));
-    const double s13sq = clamp01(p[1] + (vcol == 1 ? vdelta : 0.0));
-    const double dm21 = p[2] + (vcol == 2 ? vdelta : 0.0);
+    const double s12sq = clamp01(p[0]);
+    const double s13sq = clamp01(p[1]);
+    const double dm21 = p[2];
     const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq;
     const double c13 = sqrt01(c13sq);
     const double u1 = sqrt01(c12sq) * c13, u2 = sqrt01(s12sq) * c13, u3 = sqrt01(s13sq);
     const double p0 = c12sq * c13sq;                     // P_0 = c12^2 c13^2 (osc.jl:196)
     const double c2 = 1.0 - 2.0 * s12sq;                 // cos(2 theta12)
 
-    // Finite-difference variants of an earth norm (gradient path) only move the rows whose paths cross that layer;
-    // the others are written as 0 in both the + and the - copy (the gradient only uses their difference), and a layer
-    // no path reaches costs nothing at all.
-    const int vlay = (T.earth_unc && vcol >= SOLAROSC_N_FIXED_PARAMS) ? vcol - SOLAROSC_N_FIXED_PARAMS : -1;
-    if (vlay >= T.n_ltbl) {
-        for (int t = threadIdx.x; t < (1 + T.n_cosz) * cb; t += blockDim.x) sink.put(t / cb, i0 + t % cb, 0.0, 0.0);
-        return;
-    }
     SOLAROSC_PH(1);
     // ---- phase 1a: one eigen-system per (fine energy, layer)  (osc.jl:466-470, 370-388) --------
     // two entries per thread and pass: make_entry is branch-free, so the two dependency chains interleave
@@ -238,8 +220,8 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
         const int tb = min(t + (int)blockDim.x, ne * nl - 1);   // a thread without a second entry repeats the last one
         const int ka = t / ne, ela = t - ka * ne, kb = tb / ne, elb = tb - kb * ne;
         const double ea = T.e_calc[2 * i0 + ela], eb = T.e_calc[2 * i0 + elb];
-        const double na = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + ka] + (vcol == SOLAROSC_N_FIXED_PARAMS + ka ? vdelta : 0.0) : 1.0;
-        const double nb = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + kb] + (vcol == SOLAROSC_N_FIXED_PARAMS + kb ? vdelta : 0.0) : 1.0;
+        const double na = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + ka] : 1.0;
+        const double nb = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + kb] : 1.0;
         // lookup = earth_norm .* earth_lookup (propagation_osc.jl:60)
         const double aa = na * T.earth_lookup[ka] * ea, ab = nb * T.earth_lookup[kb] * eb;
         double enta[kEntry], entb[kEntry];
@@ -324,10 +306,6 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
         const int item = wi * 32 + lane;
         if (item >= n_items) continue;
         const int zr = (int)((item + 0.5) * inv_cb), j = item - zr * cb;   // exact: item < 2^31, cb >= 1
-        if (vlay >= 0 && !((T.row_layers[zr] >> vlay) & 1u)) {
-            sink.put(1 + G.row_order[zr], i0 + j, 0.0, 0.0);
-            continue;
-        }
         double acc8 = 0.0, acch = 0.0;
         const double* t0 = tbl + (size_t)j * kEntry;           // even fine energy of this coarse bin, layer 0
         const double* t1 = t0 + (size_t)cbs * kEntry;          // odd fine energy
@@ -383,16 +361,9 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
            double* __restrict__ osc_out /* [n_points][2][1+n_cosz][n_etrue] */,
            double* __restrict__ p1e_out /* [n_points][n_paths][n_e] or nullptr */) {
     extern __shared__ __align__(16) double smem[];
-    const int g = blockIdx.x / L.n_chunks;               // output slot: (point, variant)
+    const int g = blockIdx.x / L.n_chunks;               // oscillation point
     const int chunk = blockIdx.x - g * L.n_chunks;
-    const int point = g / L.n_var, var = g - point * L.n_var;
-    const double* p = params + (size_t)point * L.point_step * L.param_stride;
-    int vcol = -1;
-    double vdelta = 0.0;
-    if (var > 0) {
-        vcol = grad_dir_col((var - 1) >> 1);
-        vdelta = ((var - 1) & 1) ? -grad_step(vcol, p) : grad_step(vcol, p);
-    }
+    const double* p = params + (size_t)g * L.point_step * L.param_stride;
     const int i0 = chunk * L.cb;                         // first coarse energy bin of this CTA
     const int cb = min(L.cb, T.n_etrue - i0);            // coarse bins handled here
     const int nrow = 1 + T.n_cosz;
@@ -401,8 +372,8 @@ osc_kernel(const DevTables T, const OscLaunch L, const double* __restrict__ para
     const SegTables G = stage_seg_tables(T, smem + osc_smem_doubles(T.n_ltbl, L.cb), L.seg_smem != 0);
     GlobalSink sink{osc_out + (size_t)g * 2 * nrow * T.n_etrue, osc_out + ((size_t)g * 2 + 1) * nrow * T.n_etrue, T.n_etrue};
     double* p1e = p1e_out ? p1e_out + (size_t)g * T.n_paths * T.n_e : nullptr;
-    if (L.seg_smem) osc_stage<true>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink, vcol, vdelta);
-    else osc_stage<false>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink, vcol, vdelta);
+    if (L.seg_smem) osc_stage<true>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink);
+    else osc_stage<false>(T, G, p, i0, cb, L.cb, tbl, msw, p1e, sink);
 }
 
 // ------------------------------------------------------------------------------------------

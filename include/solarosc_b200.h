@@ -206,11 +206,15 @@ int solarosc_eval_llh_grouped(solarosc_handle *h, const double *params, size_t n
 int solarosc_eval_llh_multi(solarosc_handle *const *hs, size_t n_handles, const double *params, size_t n_points,
                             size_t group, double *out_lnl, uint32_t *out_flags);
 
-/* lnL and d lnL / d params for every point: out_grad[b*P + k] = d lnL_b / d params[b][k].  Fluxes, cross-section
- * and background norms are differentiated analytically (reverse mode through the fold); the oscillation columns
- * (0..2 and earth_norm_*) use central differences of the oscillation stage (relative accuracy ~1e-6).  Columns
- * the likelihood does not depend on ({det}_ES_bg_norm_2.., which the reference never reads) get 0, as does every
- * column of a point whose earth norms are out of bounds (lnL = -Inf). */
+/* lnL and d lnL / d params for every point: out_grad[b*P + k] = d lnL_b / d params[b][k], every column exact to
+ * rounding like the reference's ForwardDiff duals (mcmc.jl:102-103).  Fluxes, cross-section and background norms are
+ * differentiated in reverse through the Poisson sum and the response fold (grad_kernel); the oscillation columns
+ * (0..2 and earth_norm_*) by an adjoint sweep through the layered Earth propagation and the analytic derivative of the
+ * MSW factors (adjoint_kernel; against 40-digit differentiation of the reference formula: 1e-13 relative,
+ * tests/test_adjoint_highprec.py).  sin2_th12 and sin2_th13 are clamped to [0, 1] by the reference
+ * (propagation_osc.jl:30-36): their columns are 0 outside the open interval.  Columns the likelihood does not depend
+ * on ({det}_ES_bg_norm_2.., which the reference never reads) get 0, as does every column of a point whose earth
+ * norms are out of bounds (lnL = -Inf).  Exclusive, non-angular analysis. */
 int solarosc_eval_llh_grad(solarosc_handle *h, const double *params, size_t n_points, double *out_lnl,
                            double *out_grad, uint32_t *out_flags);
 
