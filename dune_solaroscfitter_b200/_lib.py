@@ -14,14 +14,16 @@ from . import abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SOLAROSC_LIB") or os.path.join(_PKG, "libsolarosc_b200.so")
-_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_pipe.cuh", "solarosc_grad.cuh", "solarosc_adjoint.cuh", "solarosc_adjoint_math.cuh", "solarosc_general.cuh", "solarosc_setup.cuh", "solarosc_batcher.hpp")]
+_SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("solarosc_b200.cu", "solarosc_device.cuh", "solarosc_kernels.cuh", "solarosc_pipe.cuh", "solarosc_grad.cuh", "solarosc_adjoint.cuh", "solarosc_adjoint_math.cuh", "solarosc_general.cuh", "solarosc_setup.cuh", "solarosc_batcher.hpp", "solarosc_comm.hpp")]
 _SOURCES.append(os.path.join(_ROOT, "include", "solarosc_b200.h"))
 
 EXPORTS = (
     "solarosc_abi_version", "solarosc_create", "solarosc_destroy", "solarosc_last_error", "solarosc_n_params",
-    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_multi", "solarosc_eval_llh_grad", "solarosc_eval_rates",
+    "solarosc_set_data", "solarosc_eval_llh", "solarosc_eval_llh_grouped", "solarosc_eval_llh_multi", "solarosc_eval_llh_grad", "solarosc_eval_rates", "solarosc_eval_cc_incl_spectrum",
     "solarosc_eval_perbin", "solarosc_eval_asymmetry", "solarosc_eval_derived", "solarosc_eval_oscprobs", "solarosc_eval_p1e", "solarosc_eval_llh_device",
     "solarosc_poisson_llh", "solarosc_set_timing", "solarosc_last_timing", "solarosc_last_fused", "solarosc_measure_fp64_peak",
+    "solarosc_comm_unique_id", "solarosc_comm_init", "solarosc_comm_destroy", "solarosc_shard_bounds", "solarosc_eval_llh_sharded",
+    "solarosc_eval_llh_sharded_device",
     "solarosc_batcher_create", "solarosc_batcher_create_with", "solarosc_batcher_eval", "solarosc_batcher_leave",
     "solarosc_batcher_stats", "solarosc_batcher_destroy",
     "solarosc_setup_bin_index", "solarosc_setup_bin_index_device", "solarosc_setup_histogram",
@@ -40,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _SOURCES)
     if force or stale:
         cmd = ["nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-Xcompiler", "-fPIC,-O3", "-shared", "-o", LIB_PATH, _SOURCES[0], "-lcudart"]
+               "-Xcompiler", "-fPIC,-O3", "-shared", "-o", LIB_PATH, _SOURCES[0], "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             print(r.stdout, r.stderr)
@@ -73,6 +75,13 @@ def load():
     L.solarosc_eval_llh_grad.argtypes = [H, dp, sz, dp, dp, up]
     L.solarosc_eval_rates.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp, dp, dp]
     L.solarosc_eval_perbin.argtypes = [H, C.c_int, dp, sz, dp, dp, dp, dp]
+    L.solarosc_eval_cc_incl_spectrum.argtypes = [H, C.c_int, dp, sz, dp]
+    L.solarosc_comm_unique_id.argtypes = [C.c_void_p]
+    L.solarosc_comm_init.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    L.solarosc_comm_destroy.argtypes = [H]
+    L.solarosc_shard_bounds.argtypes = [sz, sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    L.solarosc_eval_llh_sharded.argtypes = [H, dp, sz, sz, dp, up]
+    L.solarosc_eval_llh_sharded_device.argtypes = [H, C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, C.c_void_p]
     L.solarosc_eval_asymmetry.argtypes = [H, C.c_int, dp, sz, dp, dp]
     L.solarosc_eval_llh_multi.argtypes = [C.POINTER(H), sz, dp, sz, sz, dp, C.POINTER(C.c_uint32)]
     L.solarosc_eval_derived.argtypes = [H, C.c_int, dp, sz] + [dp] * 11

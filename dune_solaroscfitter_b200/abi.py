@@ -10,6 +10,7 @@ from typing import Any, Dict, List, Mapping, Optional, Sequence
 import numpy as np
 
 ABI_VERSION = 3
+COMM_ID_BYTES = 128
 MAX_LAYERS = 8
 MAX_BG = 8
 N_FIXED_PARAMS = 8
@@ -115,6 +116,7 @@ class PackedTables:
         self.ext_array = (DetectorExt * n_det)()
         self.n_norms = []
         self.n_cos = []
+        self.inclusive = []
         for d, src in enumerate(detectors):
             ds = self.det_array[d]
             ds.es_mode = int(src.get("es_mode", es_mode)) if hasattr(src, "get") else int(es_mode)
@@ -139,6 +141,7 @@ class PackedTables:
             incl = int(src["inclusive"]) if "inclusive" in src else 0
             ang = int(src["angular"]) if "angular" in src else 0
             self.n_cos.append(int(src["n_cos"]) if ang else 1)
+            self.inclusive.append(incl)
             if incl or ang:
                 x = self.ext_array[d]
                 x.inclusive, x.angular, x.n_cos = incl, ang, int(src["n_cos"]) if ang else 0

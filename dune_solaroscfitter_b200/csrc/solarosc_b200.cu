@@ -50,8 +50,11 @@ struct ArgFail {
 
 }  // namespace
 
+struct solarosc_comm_state;
+
 struct solarosc_handle {
     solarosc_config cfg{};
+    solarosc_comm_state* comm = nullptr;   // NCCL communicator of the sharded calls (solarosc_comm.hpp)
     DevTables T{};
     int device = 0, sm_count = 148, chunk = 4096, P = 0;
     int max_ereco = 0;
@@ -1097,6 +1100,7 @@ solarosc_handle* solarosc_create(const solarosc_tables* tables, const solarosc_c
 
 void solarosc_destroy(solarosc_handle* h) {
     if (!h) return;
+    if (h->comm) solarosc_comm_destroy(h);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
@@ -1317,6 +1321,29 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             }
         }
         if (scalars) std::memcpy(scalars, acc.data(), 21 * sizeof(double));
+        return (int)SOLAROSC_OK;
+    });
+}
+
+int solarosc_eval_cc_incl_spectrum(solarosc_handle* h, int det, const double* params, size_t n, double* out) {
+    return guarded(h, [&]() {
+        REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
+        REQUIRE(h->T.det[det].incl != 0, "CC_incl_spectrum exists for the inclusive and semi-inclusive analyses only (the reference returns nothing otherwise)");
+        if (n == 0) return (int)SOLAROSC_OK;
+        REQUIRE(params && out, "params and out must not be NULL");
+        const int nE = h->n_es[det];
+        h->ensure_scratch((size_t)h->chunk * nE * sizeof(double));
+        h->launches = 0;
+        for (size_t b0 = 0; b0 < n; b0 += h->chunk) {
+            const int nb = (int)std::min<size_t>(h->chunk, n - b0);
+            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
+            cc_incl_spectrum_kernel<<<nb, kThreads, 2 * h->T.n_etrue * sizeof(double), h->stream>>>(h->T, det, h->P, h->d_params, h->d_osc, h->d_scratch);
+            CK(cudaGetLastError());
+            ++h->launches;
+            CK(cudaMemcpyAsync(out + b0 * nE, h->d_scratch, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
         return (int)SOLAROSC_OK;
     });
 }
@@ -1597,3 +1624,4 @@ int solarosc_setup_earth_paths(const double* radius, const double* potential, si
 }  // extern "C"
 
 #include "solarosc_batcher.hpp"
+#include "solarosc_comm.hpp"

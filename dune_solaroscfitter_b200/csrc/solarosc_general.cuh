@@ -392,4 +392,43 @@ gen_llh_kernel(const DevTables T, const RatesLaunch L, const GenLaunch GL, const
     }
 }
 
+// CC_incl_spectrum (the 7th element of propagateSamples' tuple, propagation_main.jl:108-146; setup.jl:235-243 prints the
+// split of the inclusive data with it): the inclusive-CC part of the ES arrays summed over day + night rows (and over the
+// cos-scatter bins of the angular reconstruction),
+//   spectrum[j] = sa_j sum_i s_i (F8 X8[i][j] Q8[i] + Fh Xh[i][j] Qh[i]),   Q[i] = sum_rows w_row P[row][i],
+// X = f_above 0.5 eff_CCincl u_cc R_CCincl (D.xs8 / D.xsh), sa_j = sum_c BG.angular[c][j] (1 when not angular).
+// One CTA per point on the probabilities osc_kernel wrote.
+__global__ void __launch_bounds__(kThreads)
+cc_incl_spectrum_kernel(const DevTables T, int det, int param_stride, const double* __restrict__ params,
+                        const double* __restrict__ osc /* [n][2][1+n_cosz][n_etrue] */, double* __restrict__ out /* [n][n_es] */) {
+    extern __shared__ __align__(16) double smem[];
+    const DevDetector& D = T.det[det];
+    const int nT = T.n_etrue, nrow = 1 + T.n_cosz, le = 8 * ((D.n_es + 7) / 8);
+    const size_t b = blockIdx.x;
+    const double* p = params + b * param_stride;
+    const double* p8 = osc + b * 2 * nrow * nT;
+    const double* ph = p8 + (size_t)nrow * nT;
+    double* q8 = smem;          // [nT] F8 s_i Q8[i]
+    double* qh = smem + nT;     // [nT] Fh s_i Qh[i]
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+        double a8 = p8[i], ah = ph[i];                                   // day row, w = 1
+        for (int row = 1; row < nrow; ++row) {
+            const double w = T.wz[row - 1];
+            a8 = fma(w, p8[(size_t)row * nT + i], a8);
+            ah = fma(w, ph[(size_t)row * nT + i], ah);
+        }
+        const double l = D.log_e_norm[i];
+        const double sh = exp(fma(p[6], l, p[7] * (l * l))) * p[5];       // cross-section shape (propagation_osc.jl:185-196)
+        q8[i] = p[3] * sh * a8;
+        qh[i] = p[4] * sh * ah;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < D.n_es; j += blockDim.x) {
+        double acc = 0.0;
+        if (D.xs8)
+            for (int i = 0; i < nT; ++i) acc = fma(q8[i], D.xs8[(size_t)i * le + j], fma(qh[i], D.xsh[(size_t)i * le + j], acc));
+        out[b * D.n_es + j] = D.ang ? acc * D.ang_sb[j] : acc;
+    }
+}
+
 }  // namespace solarosc

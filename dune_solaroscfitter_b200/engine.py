@@ -49,6 +49,7 @@ class SolarOscEngine:
         self.col_major = bool(col_major)
         self.n_etrue, self.n_cosz, self.n_paths = self.packed.n_etrue, self.packed.n_cosz, self.packed.n_paths
         self.device = device
+        self.rank, self.world = 0, 1
 
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -139,6 +140,16 @@ class SolarOscEngine:
                                                 _dp(r["CC_day"]), _dp(r["CC_night"]), _dp(r["BG_ES_tot"]), _dp(r["BG_CC_tot"])))
         return r
 
+    def eval_cc_incl_spectrum(self, params, det: int = 0) -> Optional[np.ndarray]:
+        """CC_incl_spectrum [n, n_ereco_es] (7th element of propagateSamples, propagation_main.jl:108-146); None for a
+        detector of the exclusive analysis, where the reference returns ``nothing``."""
+        if not self.packed.inclusive[det]:
+            return None
+        p = self._params(params)
+        out = np.empty((len(p), self.packed.n_ereco[det][0]))
+        self._check(self._L.solarosc_eval_cc_incl_spectrum(self._h, det, _dp(p), len(p), _dp(out)))
+        return out
+
     def eval_perbin(self, params, det: int = 0) -> Dict[str, np.ndarray]:
         p = self._params(params)
         n = len(p)
@@ -209,6 +220,55 @@ class SolarOscEngine:
         """Enqueue on device-resident buffers (raw pointers, e.g. ``tensor.data_ptr()``); no synchronisation."""
         self._check(self._L.solarosc_eval_llh_device(self._h, C.c_void_p(d_params_ptr), n, group, C.c_void_p(d_lnl_ptr),
                                                      C.c_void_p(d_flags_ptr or None), C.c_void_p(stream_ptr or None)))
+
+    # -- one process per GPU: NCCL communicator inside the library ----------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes (an ncclUniqueId) from rank 0, to be handed to every rank by the host's own means."""
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        st = _lib.load().solarosc_comm_unique_id(buf)
+        if st != abi.OK:
+            raise SolarOscError(st, "solarosc_comm_unique_id failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Collective: every rank calls this with the same id (solarosc_comm_init)."""
+        self._check(self._L.solarosc_comm_init(self._h, C.c_char_p(unique_id), rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_init_from_torch(self):
+        """Bootstrap the library's communicator over an initialised torch.distributed group: rank 0 draws the id and
+        broadcasts its bytes (plumbing only; the gather itself is the library's own NCCL call)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(abi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def shard_bounds(self, n_total: int, group: int = 1, rank: Optional[int] = None, world: Optional[int] = None):
+        lo, hi = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._L.solarosc_shard_bounds(n_total, group, self.rank if rank is None else rank,
+                                                  self.world if world is None else world, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def eval_llh_sharded(self, params_local, n_total: int, group: int = 1, return_flags: bool = False):
+        """This rank's rows in, lnL of all n_total points out (all-gathered over NCCL inside the library)."""
+        p = self._params(params_local) if len(params_local) else np.empty((0, self.n_params))
+        out, fl = np.empty(n_total), np.zeros(n_total, dtype=np.uint32)
+        st = self._L.solarosc_eval_llh_sharded(self._h, _dp(p), n_total, group, _dp(out), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
+        if st != abi.ERR_NEGATIVE_RATE:
+            self._check(st)
+        return (out, fl) if return_flags else out
+
+    def eval_llh_sharded_device(self, d_params_local_ptr: int, n_total: int, d_lnl_all_ptr: int, d_flags_all_ptr: int = 0,
+                                group: int = 1, stream_ptr: int = 0):
+        self._check(self._L.solarosc_eval_llh_sharded_device(self._h, C.c_void_p(d_params_local_ptr or None), n_total, group,
+                                                             C.c_void_p(d_lnl_all_ptr), C.c_void_p(d_flags_all_ptr or None),
+                                                             C.c_void_p(stream_ptr or None)))
 
     def poisson_llh(self, expected, measured):
         e = np.ascontiguousarray(np.atleast_2d(expected), dtype=np.float64)

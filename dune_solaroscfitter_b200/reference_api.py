@@ -134,7 +134,7 @@ class SolarOscSession:
     def propagateSamples(self, unoscillatedSample=None, responseMatrices=None, params=None, solarModel=None,
                          bin_edges=None, raw_backgrounds=None, det_flags=None, *, precomputed_osc=None,
                          verbose=False):
-        """7-tuple of propagation_main.jl:155-156 for the exclusive, non-angular branch.
+        """7-tuple of propagation_main.jl:155-156 (every branch; CC_incl_spectrum is None in the exclusive analysis).
 
         The table arguments are accepted for signature compatibility; the tables in use are the ones
         the session was created with.  ``precomputed_osc`` is accepted and not needed: the oscillation
@@ -144,9 +144,11 @@ class SolarOscSession:
         if det_flags is not None:
             name = det_flags["det_name"] if isinstance(det_flags, Mapping) else getattr(det_flags, "det_name")
             det = self.det_names.index(name)
-        r = self.engine.eval_rates(self.pack_many(params), det)
+        pm = self.pack_many(params)
+        r = self.engine.eval_rates(pm, det)
+        spec = self.engine.eval_cc_incl_spectrum(pm, det)
         return (r["ES_day"][0], r["CC_day"][0], r["ES_night"][0], r["CC_night"][0],
-                r["BG_ES_tot"][0], r["BG_CC_tot"][0], None)
+                r["BG_ES_tot"][0], r["BG_CC_tot"][0], None if spec is None else spec[0])
 
     def expected_rates_batch(self, params, det: int = 0) -> Dict[str, np.ndarray]:
         return self.engine.eval_rates(self.pack_many(params), det)

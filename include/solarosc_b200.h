@@ -30,6 +30,7 @@
  *   solarosc_eval_rates    expected_rates, likelihood_core.jl:17-35 == propagateSamples,
  *                          propagation_main.jl:56-157 (all branches: exclusive, inclusive, semi-inclusive,
  *                          each with or without the angular ES reconstruction)
+ *   solarosc_eval_cc_incl_spectrum  the 7th element of that tuple, propagation_main.jl:108-146
  *   solarosc_eval_perbin   make_perbin_likelihood, likelihood_builder.jl:261-333
  *   solarosc_eval_asymmetry the per-sample D/N asymmetry of derive_variables_from_chain.jl:236-258
  *   solarosc_eval_derived  the replay loop of derive_variables_from_chain.jl:260-444 over a block of chain samples
@@ -206,6 +207,30 @@ int solarosc_eval_llh_grouped(solarosc_handle *h, const double *params, size_t n
 int solarosc_eval_llh_multi(solarosc_handle *const *hs, size_t n_handles, const double *params, size_t n_points,
                             size_t group, double *out_lnl, uint32_t *out_flags);
 
+/*
+ * One process per GPU: every rank creates its handle on its own device, the ranks share an
+ * NCCL communicator, each evaluates its contiguous slice of the batch and the per-point lnL / flag vectors are
+ * all-gathered device-to-device over NVLink -- the only collective of the path, 12 bytes per point.  NCCL is bound at run
+ * time (dlopen of libnccl.so.2); without it these calls return SOLAROSC_ERR_CUDA and everything else works.
+ *
+ *   solarosc_comm_unique_id   rank 0: 128 bytes (an ncclUniqueId) to hand to every rank by the host's own means
+ *                             (MPI.jl bcast, a shared file, torch.distributed ...)
+ *   solarosc_comm_init        collective: every rank, same id, its rank and the world size
+ *   solarosc_shard_bounds     rows [lo, hi) of a rank: whole groups, dealt as evenly as possible, earlier ranks first
+ *   solarosc_eval_llh_sharded every rank passes ITS rows (params_local = the rows solarosc_shard_bounds gives it, host
+ *                             buffer) and receives the lnL / flags of ALL n_total points
+ *   solarosc_eval_llh_sharded_device  the same with device pointers on `stream`, returning without synchronising
+ */
+#define SOLAROSC_COMM_ID_BYTES 128
+int solarosc_comm_unique_id(void *id_out);
+int solarosc_comm_init(solarosc_handle *h, const void *id, int rank, int world_size);
+int solarosc_comm_destroy(solarosc_handle *h);
+int solarosc_shard_bounds(size_t n_total, size_t group, int rank, int world_size, size_t *lo, size_t *hi);
+int solarosc_eval_llh_sharded(solarosc_handle *h, const double *params_local, size_t n_total, size_t group,
+                              double *out_lnl, uint32_t *out_flags);
+int solarosc_eval_llh_sharded_device(solarosc_handle *h, const double *d_params_local, size_t n_total, size_t group,
+                                     double *d_lnl_all, uint32_t *d_flags_all, void *stream);
+
 /* lnL and d lnL / d params for every point: out_grad[b*P + k] = d lnL_b / d params[b][k], every column exact to
  * rounding like the reference's ForwardDiff duals (mcmc.jl:102-103).  Fluxes, cross-section and background norms are
  * differentiated in reverse through the Poisson sum and the response fold (grad_kernel); the oscillation columns
@@ -223,6 +248,13 @@ int solarosc_eval_llh_grad(solarosc_handle *h, const double *params, size_t n_po
  *   cc_day, cc_night likewise, bg_es [n][n_ereco_es], bg_cc [n][n_ereco_cc]. */
 int solarosc_eval_rates(solarosc_handle *h, int det, const double *params, size_t n_points, double *es_day,
                         double *es_night, double *cc_day, double *cc_night, double *bg_es, double *bg_cc);
+
+/* CC_incl_spectrum, the 7th element of propagateSamples' tuple (propagation_main.jl:108-146; setup.jl:235-243 uses it
+ * to print the ES / CC / background split of the inclusive data): the inclusive-CC part of the ES arrays summed over the
+ * day vector and every night row (and the cos-scatter bins), times CC_split.above in the semi-inclusive analysis.
+ * out [n][n_ereco_es].  Detectors of the exclusive analysis have none (the reference returns `nothing`):
+ * SOLAROSC_ERR_ARG. */
+int solarosc_eval_cc_incl_spectrum(solarosc_handle *h, int det, const double *params, size_t n_points, double *out);
 
 /* Per-bin Poisson terms of detector det, shaped like the data (zeros outside idx..n-1, -Inf
  * everywhere for a point whose earth norms are out of bounds). */

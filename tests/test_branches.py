@@ -78,8 +78,13 @@ def test_general_fold_matches_the_oracle(tables, branches, draw, incl, ang):
         got = e.eval_rates(p)
         lnl = e.eval_llh(p)
         many = e.eval_llh(np.tile(p, (60, 1)))          # several chunks' worth of CTAs
+        spec = e.eval_cc_incl_spectrum(p)
     for i in range(len(p)):
         ref = O.propagate_samples(p[i], t)
+        if incl == 0:                                   # CC_incl_spectrum: `nothing` in the exclusive analysis
+            assert spec is None and ref["CC_incl_spectrum"] is None
+        else:                                           # propagation_main.jl:108-146
+            assert np.max(np.abs(spec[i] - ref["CC_incl_spectrum"]) / np.maximum(np.abs(ref["CC_incl_spectrum"]), 1e-300)) < 1e-9
         for k in ("ES_day", "ES_night", "CC_day", "CC_night", "BG_ES_tot", "BG_CC_tot"):
             a, b = got[k][i], ref[k]
             assert a.shape == b.shape, (k, a.shape, b.shape)

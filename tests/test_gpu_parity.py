@@ -277,3 +277,19 @@ def test_parameter_corners(engine, coracle, tables):
     for k in ("ES_day", "ES_night", "CC_day", "CC_night"):
         scale = np.maximum(np.abs(rr[k]), 1e-9 * np.max(np.abs(rr[k])))
         assert np.max(np.abs(r[k] - rr[k]) / scale) < 1e-9, k
+
+
+def test_single_rank_communicator_gathers_the_same_values(tables, asimov, draw):
+    """The in-library NCCL path with a one-rank communicator: solarosc_eval_llh_sharded == solarosc_eval_llh (the
+    multi-rank run is tools/sharded_check.py under torchrun)."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    p = draw(tables, 27 * 40, seed=91)
+    p[5, 9] = 2.5
+    with SolarOscEngine(tables, data=asimov) as e:
+        e.comm_init(e.comm_unique_id(), 0, 1)
+        assert e.shard_bounds(len(p), 27) == (0, len(p))
+        a, fa = e.eval_llh_sharded(p, len(p), return_flags=True)
+        b, fb = e.eval_llh(p, return_flags=True)
+        g = e.eval_llh_sharded(p, len(p), group=27)
+        gb = e.eval_llh(p, group=27)
+    assert np.array_equal(a, b) and np.array_equal(fa, fb) and np.array_equal(g, gb)

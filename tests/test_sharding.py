@@ -66,3 +66,31 @@ def test_two_rank_gather_matches_single_process(n_groups, group):
         assert np.array_equal(out, want)            # every rank holds the full, ordered vector
         lo, hi = shard_bounds(len(params), 2, r, group)
         assert calls == ([hi - lo] if hi > lo else [])   # and evaluated only its own slice
+
+
+def test_library_shard_bounds_match_the_python_ones():
+    """solarosc_shard_bounds (the split the in-library NCCL gather uses) against sharding.shard_bounds, and the inverse
+    map row -> rank that the unpadding kernel computes (csrc/solarosc_comm.hpp), restated here."""
+    import ctypes as C
+    from dune_solaroscfitter_b200 import _lib
+    from dune_solaroscfitter_b200.sharding import shard_bounds
+    L = _lib.load()
+    for n_groups in (0, 1, 5, 8, 27, 1000, 262144):
+        for group in (1, 27):
+            for world in (1, 2, 3, 4, 8):
+                n = n_groups * group
+                owner = np.full(n, -1)
+                for r in range(world):
+                    lo, hi = C.c_size_t(), C.c_size_t()
+                    assert L.solarosc_shard_bounds(n, group, r, world, C.byref(lo), C.byref(hi)) == 0
+                    assert (lo.value, hi.value) == shard_bounds(n, world, r, group)
+                    owner[lo.value:hi.value] = r
+                if n == 0:
+                    continue
+                base, extra = divmod(n_groups, world)
+                gi = np.arange(n) // group
+                cut = extra * (base + 1)
+                r = np.where(gi < cut, gi // (base + 1), extra + (gi - cut) // max(base, 1))
+                assert np.array_equal(r, owner)
+    lo, hi = C.c_size_t(), C.c_size_t()
+    assert L.solarosc_shard_bounds(10, 3, 0, 2, C.byref(lo), C.byref(hi)) == 1      # n not a multiple of group
