@@ -18,12 +18,14 @@ is passed and returned as it lies in Julia memory.  Batched outputs get the batc
 module B200Osc
 
 using Base: @ccall
+import ForwardDiff
+import DensityInterface
 
 const libb200 = joinpath(@__DIR__, "libsolarosc_b200.so")
 const Handle = Ptr{Cvoid}
 const handle = Ref{Handle}(C_NULL)
 
-const ABI_VERSION = Int32(2)
+const ABI_VERSION = Int32(3)
 const N_FIXED = 8
 
 # ---- C structs (include/solarosc_b200.h) ---------------------------------------------------------
@@ -64,6 +66,7 @@ end
 
 struct CConfig
     abi_version::Int32; device::Int32; fast::Int32; earth_uncertainty::Int32; col_major::Int32; max_batch::Int32
+    night_only::Int32; reserved::Int32
 end
 
 # Parameter order fixed at create; filled by init_engine
@@ -72,6 +75,9 @@ const n_layers = Ref(0)
 const n_norms = Tuple{Int,Int}[]
 const earth_unc = Ref(true)
 const xsec_norm_true = Ref(1.0)
+const n_cosz = Ref(0)       # coarse zenith bins / true-energy bins of the handle (shapes of the oscillation outputs)
+const n_etrue = Ref(0)
+const det_shapes = Dict{String,NamedTuple}()   # det_name => (nes, ncc, ncos, inclusive)
 
 f64(x) = collect(Float64, vec(x))
 i32(x) = collect(Int32, vec(x))
@@ -86,7 +92,7 @@ detector loop; the counterpart of `nuFastOsc.init_engines` (nuFast_interface.jl:
 """
 function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarModel, detector_outputs,
                      detector_configs; fast::Bool, earthUncertainty::Bool, cc_xsec_norm_true::Float64=1.0,
-                     n_cosz_sub::Int=1, device::Int=0, max_batch::Int=0)
+                     n_cosz_sub::Int=1, device::Int=0, max_batch::Int=0, night_only::Bool=false)
     keep = Any[]                                   # everything the C structs point into
     hold(x) = (push!(keep, x); pointer(x))
 
@@ -108,6 +114,10 @@ function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarM
         raw_cc = isempty(bg.CC) ? Float64[] : reduce(vcat, f64.(bg.CC))
         push!(det_names, name)
         push!(n_norms, (count(!=(0), bg.ES_par_counts), count(!=(0), bg.CC_par_counts)))
+        let dc = detector_configs[name]
+            det_shapes[name] = (nes=nes, ncc=ncc, ncos=dc.angular_reco ? r.bins.cos_scatter.bin_number : 1,
+                                inclusive=dc.inclusive_analysis || dc.semi_inclusive_analysis)
+        end
         # the other analysis branches of this detector (det_flags of setup.jl:140-150, tables of response.jl:111-236)
         det = detector_configs[name]
         ext = Ptr{CDetectorExt}(C_NULL)
@@ -146,7 +156,7 @@ function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarM
         solarModel.avgNeBoron, solarModel.avgNeHep,
         hold(f64(solarModel.n_e)), hold(f64(solarModel.prodFractionBoron)), hold(f64(solarModel.prodFractionHep)),
         cc_xsec_norm_true, pointer(dets))
-    cfg = CConfig(ABI_VERSION, device, fast, earthUncertainty, 1, max_batch)
+    cfg = CConfig(ABI_VERSION, device, fast, earthUncertainty, 1, max_batch, night_only, 0)
     status = Ref{Cint}(0)
     GC.@preserve keep begin
         h = @ccall libb200.solarosc_create(Ref(tables)::Ref{CTables}, Ref(cfg)::Ref{CConfig},
@@ -156,6 +166,7 @@ function init_engine(E_calc, earth_paths, earth_lookup, exposure_weights, solarM
                          unsafe_string(@ccall libb200.solarosc_last_error(C_NULL::Handle)::Cstring))
     handle[] = h
     n_layers[] = length(earth_lookup); earth_unc[] = earthUncertainty; xsec_norm_true[] = cc_xsec_norm_true
+    n_cosz[] = length(exposure_weights); n_etrue[] = length(E_calc) ÷ 2
     return h
 end
 
@@ -211,8 +222,80 @@ function total_llh_batch(params; group::Int=1)
     return out
 end
 
-"Drop-in for `total_llh(parameters)` (likelihood_main.jl:30-35)."
-total_llh(parameters) = total_llh_batch([parameters])[1]
+"""
+    column_symbols(p) -> Vector{Union{Symbol,Nothing}}
+
+The field of the NamedTuple `p` that feeds each column of `pack(p)` (`nothing` where `pack` falls back to a constant):
+the bookkeeping the chain rule of the Dual method below needs.
+"""
+function column_symbols(p)
+    pick(prefix) = sort([f for f in keys(p) if startswith(string(f), prefix)], by=string)
+    cols = Union{Symbol,Nothing}[:sin2_th12, :sin2_th13, :dm2_21, :integrated_8B_flux, :integrated_HEP_flux,
+                                 hasproperty(p, :cc_xsec_norm) ? :cc_xsec_norm : nothing,
+                                 hasproperty(p, :cc_xsec_tilt) ? :cc_xsec_tilt : nothing,
+                                 hasproperty(p, :cc_xsec_curv) ? :cc_xsec_curv : nothing]
+    earth_unc[] && append!(cols, pick("earth_norm_"))
+    for (name, (nes, ncc)) in zip(det_names, n_norms)
+        append!(cols, pick("$(name)_ES_bg_norm_")[1:nes])
+        append!(cols, pick("$(name)_CC_bg_norm_")[1:ncc])
+    end
+    return cols
+end
+
+"""
+    total_llh(parameters)
+
+Drop-in for `total_llh(parameters)` (likelihood_main.jl:30-35), including the call BAT's HMC makes of it: with
+`BATContext(ad = ADSelector(:ForwardDiff))` (mcmc.jl:102-103) the log-density is evaluated on a NamedTuple of
+`ForwardDiff.Dual`s.  A `ccall` cannot take duals, so that method strips them, asks the engine for the value AND the
+exact gradient of the point (through the chain rendezvous when one is running, so that all chains share one launch),
+and rebuilds the dual by the chain rule: partials(lnL) = sum_k dlnL/dp_k * partials(p_k).  Nothing in mcmc.jl changes:
+no new ADSelector, the same `logfuncdensity(total_llh)`.  ForwardDiff evaluates in chunks of up to 12 partials, so
+with P parameters the engine is called ceil(P / 12) times per gradient; `ForwardDiff.Chunk{P}()` makes that one.
+"""
+function total_llh(parameters::NamedTuple)
+    k = findfirst(v -> v isa ForwardDiff.Dual, values(parameters))
+    k === nothing && return total_llh_batch([parameters])[1]
+    return total_llh_dual(parameters, typeof(values(parameters)[k]))
+end
+
+function total_llh_dual(parameters::NamedTuple, ::Type{ForwardDiff.Dual{T,V,N}}) where {T,V,N}
+    vals = map(ForwardDiff.value, parameters)                     # the same NamedTuple, plain numbers
+    lnl, grad = batcher[] != C_NULL ? chain_llh_and_grad(vals) : let (l, g) = total_llh_and_grad_batch([vals]); (l[1], g[:, 1]) end
+    acc = ntuple(_ -> zero(V), Val(N))
+    for (col, name) in enumerate(column_symbols(parameters))
+        name === nothing && continue
+        x = getfield(parameters, name)
+        x isa ForwardDiff.Dual || continue
+        px = ForwardDiff.partials(x)
+        g = grad[col]
+        acc = ntuple(i -> acc[i] + g * px[i], Val(N))
+    end
+    return ForwardDiff.Dual{T}(V(lnl), ForwardDiff.Partials(acc))
+end
+
+"""
+    B200LogDensity()
+
+`likelihood_all_samples = B200Osc.B200LogDensity()` in place of `logfuncdensity(total_llh)` (likelihood_main.jl:39):
+`logdensityof(likelihood_all_samples, params)` is what llhScan.jl:97-105, mcmc.jl (through BAT) and
+derive_variables_from_chain.jl call.
+"""
+struct B200LogDensity end
+DensityInterface.DensityKind(::B200LogDensity) = DensityInterface.IsDensity()
+DensityInterface.logdensityof(::B200LogDensity, parameters) = total_llh(parameters)
+
+"""
+    logdensity_and_gradient(x::AbstractVector) -> (lnL, grad)
+
+Value and gradient on the flat parameter vector in `pack` order -- the LogDensityProblems-style entry for samplers
+that take one (AdvancedHMC used directly, or a BAT context with a custom gradient operator).
+"""
+function logdensity_and_gradient(x::AbstractVector{<:Real})
+    M = reshape(collect(Float64, x), :, 1)
+    l, g = total_llh_and_grad_batch(M)
+    return l[1], g[:, 1]
+end
 
 """
     total_llh_and_grad_batch(params) -> (lnL::Vector, grad::Matrix)   # grad is P x B
@@ -232,21 +315,42 @@ function total_llh_and_grad_batch(params)
 end
 
 # ---- rendezvous for BAT's chain threads ---------------------------------------------------------------------------
-# BAT evaluates logdensityof(likelihood, params) one point per chain thread (mcmc.jl:96-110).  Each chain thread
-# takes slot Threads.threadid() - 1; solarosc_batcher_eval blocks until all chains still running have deposited
-# their point, then one launch serves them.  With DensityInterface + ChangesOfVariables a
-# `logdensity_and_gradient` method built on chain_llh_and_grad replaces the ForwardDiff wrapper.
+# BAT evaluates logdensityof(likelihood, params) one point per chain task (mcmc.jl:96-110).  solarosc_batcher_eval
+# blocks until all chains still running have deposited their point, then one launch serves them.  A chain is a Julia
+# TASK, and tasks migrate between threads, so the slot is not Threads.threadid(): every task draws a slot from a
+# small pool the first time it evaluates, keeps it in task-local storage, and the pool reclaims the slots of finished
+# tasks (BAT starts fresh tasks for every mcmc_iterate!! call).
 const batcher = Ref{Ptr{Cvoid}}(C_NULL)
+const slot_owner = Union{Task,Nothing}[]
+const slot_lock = ReentrantLock()
 
 function start_batcher(n_chains::Int; want_grad::Bool=true, max_wait_ms::Int=0)
     batcher[] = @ccall libb200.solarosc_batcher_create(handle[]::Handle, Cint(n_chains)::Cint, Cint(want_grad)::Cint,
                                                        Cint(max_wait_ms)::Cint)::Ptr{Cvoid}
     batcher[] == C_NULL && error("solarosc_batcher_create failed")
+    lock(slot_lock) do
+        empty!(slot_owner); append!(slot_owner, fill(nothing, n_chains))
+    end
     return nothing
 end
 
-"lnL and gradient of ONE point from chain `slot` (0-based); blocks until the batch it joined has run."
-function chain_llh_and_grad(parameters, slot::Int=Threads.threadid() - 1)
+"0-based rendezvous slot of the calling task."
+function my_slot()::Int
+    tls = task_local_storage()
+    haskey(tls, :b200_slot) && return tls[:b200_slot]::Int
+    me = current_task()
+    slot = lock(slot_lock) do
+        k = findfirst(o -> o === nothing || istaskdone(o), slot_owner)
+        k === nothing && error("more concurrent chain tasks than batcher slots ($(length(slot_owner)))")
+        slot_owner[k] = me
+        k - 1
+    end
+    tls[:b200_slot] = slot
+    return slot
+end
+
+"lnL and gradient of ONE point from the calling chain task; blocks until the batch it joined has run."
+function chain_llh_and_grad(parameters, slot::Int=my_slot())
     row = pack(parameters); lnl = Ref{Cdouble}(0.0); grad = Vector{Float64}(undef, length(row)); fl = Ref{UInt32}(0)
     GC.@preserve row grad begin
         # @threadcall would hand the wait to a libuv worker; plain @ccall keeps the Julia thread parked in C, which
@@ -258,25 +362,39 @@ function chain_llh_and_grad(parameters, slot::Int=Threads.threadid() - 1)
     return lnl[], grad
 end
 
-chain_done(slot::Int=Threads.threadid() - 1) = (@ccall libb200.solarosc_batcher_leave(batcher[]::Ptr{Cvoid}, Cint(slot)::Cint)::Cint; nothing)
+function chain_done(slot::Int=my_slot())
+    @ccall libb200.solarosc_batcher_leave(batcher[]::Ptr{Cvoid}, Cint(slot)::Cint)::Cint
+    lock(slot_lock) do
+        slot_owner[slot + 1] = nothing
+    end
+    delete!(task_local_storage(), :b200_slot)
+    return nothing
+end
 stop_batcher() = (batcher[] != C_NULL && (@ccall libb200.solarosc_batcher_destroy(batcher[]::Ptr{Cvoid})::Cvoid); batcher[] = C_NULL; nothing)
 
 """
     propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc, verbose)
 
-Same signature and 7-tuple as propagation_main.jl:56-157 (exclusive, non-angular branch).  The table
-arguments are the ones the handle was created from; `precomputed_osc` is accepted and not needed.
+Same signature and 7-tuple as propagation_main.jl:56-157, every branch (exclusive, inclusive, semi-inclusive, each
+with or without the angular ES reconstruction).  The table arguments are the ones the handle was created from;
+`precomputed_osc` is accepted and not needed.
 """
 function propagateSamples(unosc, resp, params, ssm, bin_edges, raw_bg, det_flags; precomputed_osc=nothing, verbose=false)
     d = findfirst(==(det_flags.det_name), det_names) - 1
-    nes = resp.bins.ES.bin_number; ncc = resp.bins.CC.bin_number
-    ncos = det_flags.angular_reco ? resp.bins.cos_scatter.bin_number : 1
-    r = expected_rates_batch([params], d; nz=length(exposure_weights), nes=nes, ncc=ncc, ncos=ncos)
-    ES_day   = ncos > 1 ? r.ES_day[:, :, 1]      : r.ES_day[:, 1]
-    ES_night = ncos > 1 ? r.ES_night[:, :, :, 1] : r.ES_night[:, :, 1]
-    # CC_incl_spectrum (7th element, informational: setup.jl:235-243) is the CC part of the ES arrays, i.e. the
-    # difference to the exclusive rates of the same point; the engine does not return it separately
-    return ES_day, r.CC_day[:, 1], ES_night, r.CC_night[:, :, 1], r.BG_ES_tot[:, 1], r.BG_CC_tot[:, 1], nothing
+    sh = det_shapes[det_flags.det_name]
+    r = expected_rates_batch([params], d; nz=n_cosz[], nes=sh.nes, ncc=sh.ncc, ncos=sh.ncos)
+    ES_day   = sh.ncos > 1 ? r.ES_day[:, :, 1]      : r.ES_day[:, 1]
+    ES_night = sh.ncos > 1 ? r.ES_night[:, :, :, 1] : r.ES_night[:, :, 1]
+    # CC_incl_spectrum: the 7th element (propagation_main.jl:108-146); `nothing` in the exclusive analysis
+    spectrum = nothing
+    if sh.inclusive
+        M = pack_many([params]); spectrum = Vector{Float64}(undef, sh.nes)
+        GC.@preserve M spectrum begin
+            check(@ccall libb200.solarosc_eval_cc_incl_spectrum(handle[]::Handle, Cint(d)::Cint, pointer(M)::Ptr{Cdouble},
+                                                                Csize_t(1)::Csize_t, pointer(spectrum)::Ptr{Cdouble})::Cint)
+        end
+    end
+    return ES_day, r.CC_day[:, 1], ES_night, r.CC_night[:, :, 1], r.BG_ES_tot[:, 1], r.BG_CC_tot[:, 1], spectrum
 end
 
 # Rate arrays of a batch, shaped like the reference's with the batch index last: ES_day (nes, B) or, with the
@@ -301,7 +419,8 @@ end
 
 8-field NamedTuple of propagation_osc.jl:146-155 (night arrays are (n_cosz, n_Etrue)).
 """
-function compute_shared_osc_probs(params, solarModel; nz::Int, nT::Int)
+function compute_shared_osc_probs(params, solarModel)
+    nz = n_cosz[]; nT = n_etrue[]              # shapes of the handle (propagation_main.jl:47 takes no more arguments)
     M = pack_many([params])
     d8 = Vector{Float64}(undef, nT); n8 = Matrix{Float64}(undef, nz, nT)
     dh = Vector{Float64}(undef, nT); nh = Matrix{Float64}(undef, nz, nT)
@@ -356,6 +475,40 @@ function derived_block_sums(params, weights::Vector{Float64}, lref; det::Int=0, 
             pointer(bg_cc)::Ptr{Cdouble}, pointer(sc)::Ptr{Cdouble})::Cint)
     end
     return (ES_day=ES_day, CC_day=CC_day, ltot=ltot, mom_ES=mom_es, mom_CC=mom_cc, bg_mom_ES=bg_es, bg_mom_CC=bg_cc, scalars=sc)
+end
+
+# ---- one Julia process per GPU: the library's own NCCL gather ----------------------------------------------------------
+"""
+    comm_unique_id() -> Vector{UInt8}      (rank 0; hand the 128 bytes to every rank, e.g. MPI.bcast)
+    comm_init(id, rank, world)             (collective)
+    total_llh_batch_sharded(params_local, n_total; group=1) -> Vector{Float64}   (lnL of ALL n_total points on every rank)
+
+Every rank passes the rows `shard_bounds(n_total, group, rank, world)` gives it; the per-point lnL vectors are
+all-gathered device-to-device with NCCL over NVLink inside the library (solarosc_eval_llh_sharded).
+"""
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    st = GC.@preserve id @ccall libb200.solarosc_comm_unique_id(pointer(id)::Ptr{Cvoid})::Cint
+    st == 0 || error("solarosc_comm_unique_id failed (status $st): is libnccl.so.2 loadable?")
+    return id
+end
+comm_init(id::Vector{UInt8}, rank::Int, world::Int) =
+    GC.@preserve id check(@ccall libb200.solarosc_comm_init(handle[]::Handle, pointer(id)::Ptr{Cvoid}, Cint(rank)::Cint, Cint(world)::Cint)::Cint)
+function shard_bounds(n_total::Int, group::Int, rank::Int, world::Int)
+    lo = Ref{Csize_t}(0); hi = Ref{Csize_t}(0)
+    st = @ccall libb200.solarosc_shard_bounds(Csize_t(n_total)::Csize_t, Csize_t(group)::Csize_t, Cint(rank)::Cint, Cint(world)::Cint,
+                                              lo::Ref{Csize_t}, hi::Ref{Csize_t})::Cint
+    st == 0 || error("solarosc_shard_bounds: bad arguments")
+    return Int(lo[]) + 1, Int(hi[])              # 1-based inclusive range of rows
+end
+function total_llh_batch_sharded(params_local, n_total::Int; group::Int=1)
+    M = pack_many(params_local)
+    out = Vector{Float64}(undef, n_total); flags = Vector{UInt32}(undef, n_total)
+    GC.@preserve M out flags begin
+        check(@ccall libb200.solarosc_eval_llh_sharded(handle[]::Handle, pointer(M)::Ptr{Cdouble}, Csize_t(n_total)::Csize_t,
+            Csize_t(group)::Csize_t, pointer(out)::Ptr{Cdouble}, pointer(flags)::Ptr{UInt32})::Cint)
+    end
+    return out
 end
 
 end # module B200Osc
