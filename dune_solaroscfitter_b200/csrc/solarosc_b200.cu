@@ -123,6 +123,7 @@ struct solarosc_handle {
     };
     std::vector<PipePlan> pipe_plans;
     bool use_pipe = true, pipe_all = false;
+    int n_mirror = 0;           // paths that take the mirrored pair walk
     size_t smem_optin = 0;
 
     template <class Tp>
@@ -281,7 +282,29 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     T.n_ltbl = 1 + *std::max_element(app_layer.begin(), app_layer.end());
     std::vector<Seg> seg(n_seg);
     for (int i = 0; i < n_seg; ++i) seg[i] = Seg{app_len[i], app_layer[i], 0};
+    // Mirrored paths (solarosc_device.cuh): flagged on their first step, with the phase-rotation constants of the
+    // interior steps of their first half.  The bound on the phase rates (quarter turns per km) covers every eigenvalue
+    // gap of S = diag(0, dm21, dm31) + a u u^T with dm21 <= 1e-3 and earth norms <= 2 (beyond that the likelihood is
+    // -Inf anyway): gap <= dm31 + dm21 + a.  SOLAROSC_NO_MIRROR: A/B switch.
+    std::vector<double2> mir(n_seg, make_double2(0.0, 0.0));
+    h->n_mirror = 0;
+    if (std::getenv("SOLAROSC_NO_MIRROR") == nullptr) {
+        const double e_min = *std::min_element(t->e_calc, t->e_calc + T.n_e);
+        const double rho_max = *std::max_element(t->earth_lookup, t->earth_lookup + T.n_layers);
+        const double kq_max = kPhaseQT * ((kDm31 + 1e-3) / e_min + 2.0 * rho_max);
+        for (int pth = 0; pth < T.n_paths; ++pth) {
+            const int s0 = t->seg_start[pth], s1 = t->seg_start[pth + 1];
+            if (!(e_min > 0.0) || !mirror_eligible(app_layer.data(), app_len.data(), s0, s1, kq_max)) continue;
+            seg[s0].pad = 1;
+            ++h->n_mirror;
+            for (int i = 1; i < (s1 - s0) / 2; ++i) {
+                const double dr = 1.5707963267948966 * (app_len[s1 - 1 - i] - app_len[s0 + i]);
+                mir[s0 + i] = make_double2(dr, -0.5 * dr);
+            }
+        }
+    }
     T.seg = h->upload(seg.data(), n_seg);
+    T.seg_mir = h->upload(mir.data(), n_seg);
     std::vector<int> order(T.n_cosz);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_cost[a] > row_cost[b]; });

@@ -72,7 +72,8 @@ struct DevTables {
     int fast, earth_unc;
     int night_only;            // likelihoods sum the night rows only (solarosc_config.night_only)
     const double* e_calc;      // [n_e]
-    const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path
+    const Seg* seg;            // [n_seg] the APPLIED steps of all paths, path after path (pad = 1 on the first step of a mirrored path)
+    const double2* seg_mir;    // [n_seg] (dr, drh) per step: phase-rotation constants of mirrored paths
     const int2* path_se;       // [n_cosz*n_sub] (first, one-past-last) step of the paths of sorted row zr, sub-path fastest
     const int* row_order;      // [n_cosz] coarse zenith bin of sorted row zr (longest paths first)
     const unsigned* row_layers;// [n_cosz] bit k set when some path of sorted row zr crosses layer k
@@ -403,6 +404,105 @@ SOLAROSC_HD double path_p1e(const double* tbl, size_t layer_stride, const int* a
         step_last(tbl + (size_t)app_layer[s1 - 1] * layer_stride, app_len[s1 - 1], p);
     }
     return fma(p.ar, p.ar, p.ai * p.ai);   // |<nu_1|X|nu_e>|^2 (osc.jl:444)
+}
+
+// ------------------------------------------------------------------------------------------
+// Mirrored paths.  A chord through the layered Earth crosses layers k_0, k_1, .., k_h, .., k_1, k_0, and
+// every step matrix M = exp(-i S t) is complex SYMMETRIC (S is real symmetric), so the amplitude of
+// osc.jl:436-446,
+//     <nu_1| M'_0 M'_1 .. M'_{h-1}  M_h  M_{h-1} .. M_1 M_0 |u>  =  chi^T (M_h psi),
+//     psi = M_{h-1} .. M_0 u,      chi = M'_{h-1} .. M'_0 e_1        (a plain, un-conjugated dot product),
+// can be formed by walking psi (from the nu_e end) and chi (from the nu_1 end) inward TOGETHER: both cross
+// the same layer at the same energy, so they share the eigen entry, and the lengths of the two crossings of an
+// interior layer differ only by the rounding of the path builder (<= 1e-6 km), so chi's phase factors follow
+// from psi's by a second-order rotation through delta = (pi/2) dlen k (6 instructions per phase instead of a
+// 16-instruction sincos_qt; delta^3 / 6 < 1e-15 is checked per path when the handle is created -- paths that
+// are not palindromes, or whose mirrored lengths differ by more, take the generic loop).  The outermost pair
+// (the detector's depth makes its two lengths differ by metres) takes two full phase evaluations.
+// 108 FP64 instructions per interior pair of steps against 128, one table fetch instead of two.
+// ------------------------------------------------------------------------------------------
+// e^{-i (phi + delta)} from e^{-i phi}: delta = dr * k, dr = (pi/2)(len' - len), drh = -dr / 2 (both tabulated per step)
+SOLAROSC_HD void phase_shift(double s, double c, double k, double dr, double drh, double& s2, double& c2) {
+    const double d = dr * k, dh = drh * k;
+    s2 = fma(fma(s, dh, c), d, s);    // s + c d - s d^2 / 2
+    c2 = fma(fma(c, dh, -s), d, c);   // c - s d - c d^2 / 2
+}
+
+// psi <- psi + sum_n q_n (e^{-i phi_n} - 1)(q_n . psi) with the phase factors given
+SOLAROSC_HD void step_apply(const Ent& e, double s1, double c1, double s2, double c2, State& p) {
+    const double w1r = fma(e.q1z, p.cr, fma(e.q1y, p.br, e.q1x * p.ar)), w1i = fma(e.q1z, p.ci, fma(e.q1y, p.bi, e.q1x * p.ai));
+    const double w2r = fma(e.q2z, p.cr, fma(e.q2y, p.br, e.q2x * p.ar)), w2i = fma(e.q2z, p.ci, fma(e.q2y, p.bi, e.q2x * p.ai));
+    const double t1r = fma(c1, w1r, fma(s1, w1i, -w1r)), t1i = fma(c1, w1i, fma(-s1, w1r, -w1i));
+    const double t2r = fma(c2, w2r, fma(s2, w2i, -w2r)), t2i = fma(c2, w2i, fma(-s2, w2r, -w2i));
+    p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, p.ar)); p.ai = fma(e.q2x, t2i, fma(e.q1x, t1i, p.ai));
+    p.br = fma(e.q2y, t2r, fma(e.q1y, t1r, p.br)); p.bi = fma(e.q2y, t2i, fma(e.q1y, t1i, p.bi));
+    p.cr = fma(e.q2z, t2r, fma(e.q1z, t1r, p.cr)); p.ci = fma(e.q2z, t2i, fma(e.q1z, t1i, p.ci));
+}
+
+// outermost pair: psi starts from u over length len_p, chi from e_1 = (1, 0, 0) over length len_x (q_n . e_1 = q_nx)
+SOLAROSC_HD void step_first_pair(const double* ep, double len_p, double len_x, double u1, double u2, double u3, State& p, State& x) {
+    const Ent e = load_ent(ep);
+    const double2 d = reinterpret_cast<const double2*>(ep)[4];
+    double s1, c1, s2, c2;
+    step_phases(e, len_p, s1, c1, s2, c2);
+    {
+        const double t1r = fma(c1, d.x, -d.x), t1i = -s1 * d.x, t2r = fma(c2, d.y, -d.y), t2i = -s2 * d.y;
+        p.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, u1)); p.ai = fma(e.q2x, t2i, e.q1x * t1i);
+        p.br = fma(e.q2y, t2r, fma(e.q1y, t1r, u2)); p.bi = fma(e.q2y, t2i, e.q1y * t1i);
+        p.cr = fma(e.q2z, t2r, fma(e.q1z, t1r, u3)); p.ci = fma(e.q2z, t2i, e.q1z * t1i);
+    }
+    step_phases(e, len_x, s1, c1, s2, c2);
+    {
+        const double t1r = fma(c1, e.q1x, -e.q1x), t1i = -s1 * e.q1x, t2r = fma(c2, e.q2x, -e.q2x), t2i = -s2 * e.q2x;
+        x.ar = fma(e.q2x, t2r, fma(e.q1x, t1r, 1.0)); x.ai = fma(e.q2x, t2i, e.q1x * t1i);
+        x.br = fma(e.q2y, t2r, e.q1y * t1r); x.bi = fma(e.q2y, t2i, e.q1y * t1i);
+        x.cr = fma(e.q2z, t2r, e.q1z * t1r); x.ci = fma(e.q2z, t2i, e.q1z * t1i);
+    }
+}
+
+// interior pair: both states cross the layer of entry ep, psi over len, chi over len + dlen
+SOLAROSC_HD void step_pair(const double* ep, double len, double dr, double drh, State& p, State& x) {
+    const Ent e = load_ent(ep);
+    double s1, c1, s2, c2, s1x, c1x, s2x, c2x;
+    step_phases(e, len, s1, c1, s2, c2);
+    phase_shift(s1, c1, e.k1, dr, drh, s1x, c1x);
+    phase_shift(s2, c2, e.k2, dr, drh, s2x, c2x);
+    step_apply(e, s1, c1, s2, c2, p);
+    step_apply(e, s1x, c1x, s2x, c2x, x);
+}
+
+// innermost layer: |chi^T (M psi)|^2
+SOLAROSC_HD double step_middle(const double* ep, double len, State& p, const State& x) {
+    step_mid(ep, len, p);
+    const double re = fma(-x.ci, p.ci, fma(x.cr, p.cr, fma(-x.bi, p.bi, fma(x.br, p.br, fma(-x.ai, p.ai, x.ar * p.ar)))));
+    const double im = fma(x.ci, p.cr, fma(x.cr, p.ci, fma(x.bi, p.br, fma(x.br, p.bi, fma(x.ai, p.ar, x.ar * p.ai)))));
+    return fma(re, re, im * im);
+}
+
+// Whether the applied steps s0 .. s1-1 form a mirrored path the pair walk is exact for: an odd number (>= 3) of
+// steps, palindromic layers, and interior mirrored lengths so close that the second-order phase rotation is exact
+// to 1e-15 for every phase rate up to kq_max (quarter turns per km).  Host side (create).
+inline bool mirror_eligible(const int* app_layer, const double* app_len, int s0, int s1, double kq_max) {
+    const int n = s1 - s0;
+    if (n < 3 || (n & 1) == 0) return false;
+    for (int i = 0; i < n / 2; ++i) {
+        if (app_layer[s0 + i] != app_layer[s1 - 1 - i]) return false;
+        if (i == 0) continue;
+        const double delta = 1.5707963267948966 * std::fabs(app_len[s1 - 1 - i] - app_len[s0 + i]) * kq_max;
+        if (!(delta <= 1.8e-5)) return false;   // delta^3 / 6 <= 1e-15
+    }
+    return true;
+}
+
+// P1e of a mirrored path at one energy (mir[s] = (dr, drh) of applied step s, used for the interior steps of the first half)
+SOLAROSC_HD double path_p1e_mirror(const double* tbl, size_t layer_stride, const int* app_layer, const double* app_len,
+                                   const double* mir, int s0, int s1, double u1, double u2, double u3) {
+    State p, x;
+    const int h = (s1 - s0) / 2;
+    step_first_pair(tbl + (size_t)app_layer[s0] * layer_stride, app_len[s0], app_len[s1 - 1], u1, u2, u3, p, x);
+    for (int i = 1; i < h; ++i)
+        step_pair(tbl + (size_t)app_layer[s0 + i] * layer_stride, app_len[s0 + i], mir[2 * (s0 + i)], mir[2 * (s0 + i) + 1], p, x);
+    return step_middle(tbl + (size_t)app_layer[s0 + h] * layer_stride, app_len[s0 + h], p, x);
 }
 
 // MSW survival probability pieces (reference osc.jl:77-90): returns cos(2 theta12_matter)

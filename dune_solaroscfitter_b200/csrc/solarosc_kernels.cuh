@@ -152,6 +152,7 @@ struct SegTables {
     const Seg* seg;         // [n_seg] applied steps of all paths
     const int2* path_se;    // [n_cosz * n_sub] (first, one-past-last) step of the paths of sorted row zr
     const int* row_order;   // [n_cosz] zenith bin of sorted row zr
+    const double2* mir;     // [n_seg] (dr, drh) of the interior steps of the first half of a mirrored path (solarosc_device.cuh)
 };
 // One step's (layer, length).  SMEM: the tables are known to sit in shared memory, so the load is an LDS instead
 // of a generic load that has to resolve its address space first -- it feeds the table address of the next step.
@@ -161,35 +162,101 @@ __device__ __forceinline__ Seg load_seg(const SegTables& G, int s) {
     Seg r;
     long long bits;
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=d"(r.len), "=l"(bits) : "r"((uint32_t)__cvta_generic_to_shared(G.seg + s)));
-    r.layer = (int)bits; r.pad = 0;
+    r.layer = (int)bits; r.pad = (int)(bits >> 32);
+    return r;
+}
+template <bool SMEM>
+__device__ __forceinline__ double2 load_mir(const SegTables& G, int s) {
+    if (!SMEM) return G.mir[s];
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(G.mir + s)));
     return r;
 }
 
 __host__ __device__ inline size_t seg_smem_doubles(int n_seg, int n_paths, int n_cosz) {
-    return (size_t)2 * n_seg + n_paths + ((size_t)n_cosz + 1) / 2 + 1;
+    return (size_t)4 * n_seg + n_paths + ((size_t)n_cosz + 1) / 2 + 1;
 }
 
 // Copies the path tables behind `buf` (16-byte aligned; no barrier: the caller's next __syncthreads orders it).
 __device__ __forceinline__ SegTables stage_seg_tables(const DevTables& T, double* buf, bool to_smem) {
-    if (!to_smem) return SegTables{T.seg, T.path_se, T.row_order};
+    if (!to_smem) return SegTables{T.seg, T.path_se, T.row_order, T.seg_mir};
     Seg* seg = reinterpret_cast<Seg*>(buf);
-    int2* se = reinterpret_cast<int2*>(buf + 2 * T.n_seg);
-    int* order = reinterpret_cast<int*>(buf + 2 * T.n_seg + T.n_paths);
+    double2* mir = reinterpret_cast<double2*>(buf + 2 * T.n_seg);
+    int2* se = reinterpret_cast<int2*>(buf + 4 * T.n_seg);
+    int* order = reinterpret_cast<int*>(buf + 4 * T.n_seg + T.n_paths);
     // first pass with all three loads in flight before any store (one L2 round trip instead of three)
     const int t0 = threadIdx.x;
     Seg sg{};
+    double2 mr{};
     int2 pe{};
     int ro = 0;
-    if (t0 < T.n_seg) sg = T.seg[t0];
+    if (t0 < T.n_seg) { sg = T.seg[t0]; mr = T.seg_mir[t0]; }
     if (t0 < T.n_paths) pe = T.path_se[t0];
     if (t0 < T.n_cosz) ro = T.row_order[t0];
-    if (t0 < T.n_seg) seg[t0] = sg;
+    if (t0 < T.n_seg) { seg[t0] = sg; mir[t0] = mr; }
     if (t0 < T.n_paths) se[t0] = pe;
     if (t0 < T.n_cosz) order[t0] = ro;
-    for (int t = t0 + blockDim.x; t < T.n_seg; t += blockDim.x) seg[t] = T.seg[t];
+    for (int t = t0 + blockDim.x; t < T.n_seg; t += blockDim.x) { seg[t] = T.seg[t]; mir[t] = T.seg_mir[t]; }
     for (int t = t0 + blockDim.x; t < T.n_paths; t += blockDim.x) se[t] = T.path_se[t];
     for (int t = t0 + blockDim.x; t < T.n_cosz; t += blockDim.x) order[t] = T.row_order[t];
-    return SegTables{seg, se, order};
+    return SegTables{seg, se, order, mir};
+}
+
+// P1e = |<nu_1|X|nu_e>|^2 (osc.jl:436-446) of sorted path (s0, s1) at the two fine energies of a coarse bin (eigen
+// entries t0 / t1 at layer 0, ls doubles between layers).  One-layer paths: the closed form; mirrored paths
+// (flagged on their first step at create): the pair walk of solarosc_device.cuh, one fine energy after the other
+// (psi and chi are the two dependency chains in flight); anything else: the generic walk with both fine energies
+// in flight.  The (layer, length) of the next step is fetched while the current one is computed.
+template <bool SMEM>
+__device__ __forceinline__ void path_p1e_pair(const SegTables& G, const double* t0, const double* t1, int ls, int s0, int s1,
+                                              double u1, double u2, double u3, double& pe0, double& pe1) {
+    Seg sg = load_seg<SMEM>(G, s0);
+    const int k = sg.layer * ls;
+    const double len = sg.len;
+    if (s1 - s0 == 1) {
+        State pa, pb;
+        step_only(t0 + k, len, u1, pa);
+        step_only(t1 + k, len, u1, pb);
+        pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);
+        pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
+    } else if (sg.pad != 0) {
+        const double lenx = load_seg<SMEM>(G, s1 - 1).len;
+        const int h = (s1 - s0) >> 1;
+#pragma unroll 1
+        for (int par = 0; par < 2; ++par) {
+            const double* t = par ? t1 : t0;
+            State p, x;
+            Seg sn = load_seg<SMEM>(G, s0 + 1);
+            double2 mn = load_mir<SMEM>(G, s0 + 1);
+            step_first_pair(t + k, len, lenx, u1, u2, u3, p, x);
+            for (int i = 1; i < h; ++i) {
+                const int km = sn.layer * ls;
+                const double lm = sn.len, dr = mn.x, drh = mn.y;
+                sn = load_seg<SMEM>(G, s0 + i + 1);
+                mn = load_mir<SMEM>(G, s0 + i + 1);
+                step_pair(t + km, lm, dr, drh, p, x);
+            }
+            const double pe = step_middle(t + sn.layer * ls, sn.len, p, x);
+            if (par) pe1 = pe; else pe0 = pe;
+        }
+    } else {
+        State pa, pb;
+        sg = load_seg<SMEM>(G, s0 + 1);
+        step_first(t0 + k, len, u1, u2, u3, pa);
+        step_first(t1 + k, len, u1, u2, u3, pb);
+        for (int s = s0 + 1; s < s1 - 1; ++s) {
+            const int km = sg.layer * ls;
+            const double lm = sg.len;
+            sg = load_seg<SMEM>(G, s + 1);
+            step_mid(t0 + km, lm, pa);
+            step_mid(t1 + km, lm, pb);
+        }
+        const int kl = sg.layer * ls;
+        step_last(t0 + kl, sg.len, pa);
+        step_last(t1 + kl, sg.len, pb);
+        pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);
+        pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
+    }
 }
 
 __device__ __forceinline__ double sqrt_pos(double x);
@@ -312,35 +379,8 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
         for (int sub = 0; sub < T.n_sub; ++sub) {
             const int2 se = G.path_se[zr * T.n_sub + sub];
             const int s0 = se.x, s1 = se.y;
-            // Both fine energies of the bin advance through the layers together: two independent
-            // dependency chains per thread keep the FP64 pipe fed (osc_reduce_from_lookup, osc.jl:436-446).
-            // The (layer, length) of the next step is fetched while the current one is computed.
-            State pa, pb;
-            {
-                Seg sg = load_seg<SEG_SMEM>(G, s0);
-                const int k = sg.layer * ls;
-                const double len = sg.len;
-                if (s1 - s0 == 1) {
-                    step_only(t0 + k, len, u1, pa);
-                    step_only(t1 + k, len, u1, pb);
-                } else {
-                    sg = load_seg<SEG_SMEM>(G, s0 + 1);
-                    step_first(t0 + k, len, u1, u2, u3, pa);
-                    step_first(t1 + k, len, u1, u2, u3, pb);
-                    for (int s = s0 + 1; s < s1 - 1; ++s) {
-                        const int km = sg.layer * ls;
-                        const double lm = sg.len;
-                        sg = load_seg<SEG_SMEM>(G, s + 1);
-                        step_mid(t0 + km, lm, pa);
-                        step_mid(t1 + km, lm, pb);
-                    }
-                    const int kl = sg.layer * ls;
-                    step_last(t0 + kl, sg.len, pa);
-                    step_last(t1 + kl, sg.len, pb);
-                }
-            }
-            const double pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);   // |<nu_1|X|nu_e>|^2 (osc.jl:444)
-            const double pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
+            double pe0, pe1;
+            path_p1e_pair<SEG_SMEM>(G, t0, t1, ls, s0, s1, u1, u2, u3, pe0, pe1);
             if (p1e_out) {
                 double* o = p1e_out + (size_t)(G.row_order[zr] * T.n_sub + sub) * T.n_e + 2 * (i0 + j);
                 o[0] = pe0; o[1] = pe1;

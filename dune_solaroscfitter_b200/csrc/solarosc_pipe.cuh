@@ -246,32 +246,8 @@ __device__ __forceinline__ void pipe_prop_item(const DevTables& T, const SegTabl
     for (int sub = 0; sub < T.n_sub; ++sub) {
         const int2 se = G.path_se[zr * T.n_sub + sub];
         const int s0 = se.x, s1 = se.y;
-        State pa, pb;
-        {
-            Seg sg = load_seg<true>(G, s0);
-            const int k = sg.layer * ls;
-            const double len = sg.len;
-            if (s1 - s0 == 1) {
-                step_only(t0 + k, len, u1, pa);
-                step_only(t1 + k, len, u1, pb);
-            } else {
-                sg = load_seg<true>(G, s0 + 1);
-                step_first(t0 + k, len, u1, u2, u3, pa);
-                step_first(t1 + k, len, u1, u2, u3, pb);
-                for (int s = s0 + 1; s < s1 - 1; ++s) {
-                    const int km = sg.layer * ls;
-                    const double lm = sg.len;
-                    sg = load_seg<true>(G, s + 1);
-                    step_mid(t0 + km, lm, pa);
-                    step_mid(t1 + km, lm, pb);
-                }
-                const int kl = sg.layer * ls;
-                step_last(t0 + kl, sg.len, pa);
-                step_last(t1 + kl, sg.len, pb);
-            }
-        }
-        const double pe0 = fma(pa.ar, pa.ar, pa.ai * pa.ai);      // |<nu_1|X|nu_e>|^2 (osc.jl:444)
-        const double pe1 = fma(pb.ar, pb.ar, pb.ai * pb.ai);
+        double pe0, pe1;
+        path_p1e_pair<true>(G, t0, t1, ls, s0, s1, u1, u2, u3, pe0, pe1);
         const double d0 = pe0 - p0, d1 = pe1 - p0;
         acc8 += fma(msw[(size_t)2 * nT + j], d0, msw[j]) + fma(msw[(size_t)3 * nT + j], d1, msw[nT + j]);
         acch += fma(msw[(size_t)6 * nT + j], d0, msw[(size_t)4 * nT + j]) + fma(msw[(size_t)7 * nT + j], d1, msw[(size_t)5 * nT + j]);

@@ -44,6 +44,41 @@ void hm_p1e(const double* e_calc, int n_e, const int* path_start, const int* app
         }
 }
 
+// the same with the mirrored-pair walk on every eligible path (path_p1e_mirror); returns the number of eligible paths
+int hm_p1e_mirror(const double* e_calc, int n_e, const int* path_start, const int* app_layer, const double* app_len,
+                  int n_paths, const double* lookup, int nl, double s12sq_in, double s13sq_in, double dm21, double kq_max, double* p1e) {
+    const int cbs = n_e / 2;
+    std::vector<double> tbl((size_t)kEntry * nl * n_e);
+    const double s12sq = fmin(fmax(s12sq_in, 0.0), 1.0), s13sq = fmin(fmax(s13sq_in, 0.0), 1.0);
+    const double c13sq = 1.0 - s13sq, c12sq = 1.0 - s12sq, c13 = sqrt(c13sq);
+    const double u1 = sqrt(c12sq) * c13, u2 = sqrt(s12sq) * c13, u3 = sqrt(s13sq);
+    for (int k = 0; k < nl; ++k)
+        for (int el = 0; el < n_e; ++el) {
+            const int slot = (el & 1) * cbs + (el >> 1);
+            make_entry(dm21, lookup[k] * e_calc[el], e_calc[el], u1, u2, u3, tbl.data() + ((size_t)k * 2 * cbs + slot) * kEntry);
+        }
+    const int n_seg = path_start[n_paths];
+    std::vector<double> mir((size_t)2 * n_seg, 0.0);
+    int n_ok = 0;
+    for (int path = 0; path < n_paths; ++path) {
+        const int s0 = path_start[path], s1 = path_start[path + 1];
+        const bool ok = mirror_eligible(app_layer, app_len, s0, s1, kq_max);
+        n_ok += ok;
+        if (ok)
+            for (int i = 1; i < (s1 - s0) / 2; ++i) {
+                const double dr = 1.5707963267948966 * (app_len[s1 - 1 - i] - app_len[s0 + i]);
+                mir[2 * (s0 + i)] = dr; mir[2 * (s0 + i) + 1] = -0.5 * dr;
+            }
+        for (int el = 0; el < n_e; ++el) {
+            const int slot = (el & 1) * cbs + (el >> 1);
+            const double* t = tbl.data() + (size_t)slot * kEntry;
+            p1e[(size_t)path * n_e + el] = ok ? path_p1e_mirror(t, (size_t)2 * cbs * kEntry, app_layer, app_len, mir.data(), s0, s1, u1, u2, u3)
+                                              : path_p1e(t, (size_t)2 * cbs * kEntry, app_layer, app_len, s0, s1, u1, u2, u3);
+        }
+    }
+    return n_ok;
+}
+
 // P1e and its exact derivatives with respect to (sin2_th12, sin2_th13, dm2_21, earth_norm_0..nl-1) for every
 // (path, energy), with the adjoint kernel's own step functions: forward sweep, backward sweep with weight
 // c = 2 psi_1 (so that Re(beta^dagger x) = d|psi_1|^2), direction contractions per table entry.

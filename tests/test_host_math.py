@@ -32,6 +32,8 @@ def hm():
     L.hm_sincos_qt.argtypes = [dp, dp, C.c_int, dp, dp]
     L.hm_eig.argtypes = [C.c_double] * 6 + [dp, dp]
     L.hm_p1e.argtypes = [dp, C.c_int, ip, ip, dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, dp]
+    L.hm_p1e_mirror.argtypes = [dp, C.c_int, ip, ip, dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp]
+    L.hm_p1e_mirror.restype = C.c_int
     L.hm_msw_c2m.argtypes = [C.c_double] * 5
     L.hm_msw_c2m.restype = C.c_double
     return L
@@ -122,6 +124,48 @@ def test_kernel_algebra_matches_oracle_p1e(hm, tables, s12, s13, dm, norms):
               len(ss) - 1, lookup.ctypes.data_as(dp), len(lookup), s12, s13, dm, got.ctypes.data_as(dp))
     mp = O.OscPars(dm, math.asin(math.sqrt(s12)), math.asin(math.sqrt(s13)))
     ref = O.osc_prob_earth(e, mp, lookup, tables["seg_start"], tables["seg_layer"], tables["seg_length"])
+    assert np.max(np.abs(got - ref)) < 5e-12
+
+
+@pytest.mark.parametrize("s12,s13,dm,norms", CASES)
+def test_mirrored_pair_walk_matches_oracle_and_the_generic_walk(hm, tables, s12, s13, dm, norms):
+    """path_p1e_mirror (psi from the nu_e end, chi from the nu_1 end, shared eigen entries, chi's phase factors by a
+    second-order rotation of psi's) on every multi-layer path of the default binning: the oracle's P1e and, to rounding,
+    the generic step-by-step walk."""
+    ss, lay, ln = _applied(tables)
+    e = np.ascontiguousarray(tables["e_calc"])
+    lookup = np.ascontiguousarray(norms * tables["earth_lookup"])
+    args = (e.ctypes.data_as(dp), len(e), ss.ctypes.data_as(ip), lay.ctypes.data_as(ip), ln.ctypes.data_as(dp),
+            len(ss) - 1, lookup.ctypes.data_as(dp), len(lookup), s12, s13, dm)
+    got, gen = np.empty((len(ss) - 1, len(e))), np.empty((len(ss) - 1, len(e)))
+    n_ok = hm.hm_p1e_mirror(*args, 5.2, got.ctypes.data_as(dp))
+    hm.hm_p1e(*args, gen.ctypes.data_as(dp))
+    assert n_ok == int(np.sum(np.diff(ss) >= 3))          # every multi-layer chord of the default binning is mirrored
+    mp = O.OscPars(dm, math.asin(math.sqrt(s12)), math.asin(math.sqrt(s13)))
+    ref = O.osc_prob_earth(e, mp, lookup, tables["seg_start"], tables["seg_layer"], tables["seg_length"])
+    assert np.max(np.abs(got - ref)) < 5e-12
+    assert np.max(np.abs(got - gen)) < 5e-15
+
+
+def test_mirror_eligibility_rejects_what_the_rotation_cannot_cover(hm, tables):
+    """Not a palindrome, an even number of steps, or interior mirrored lengths too far apart for the second-order
+    rotation: such paths take the generic walk (hm_p1e_mirror falls back per path and still matches the oracle)."""
+    e = np.ascontiguousarray(tables["e_calc"])
+    lookup = np.ascontiguousarray(tables["earth_lookup"])
+    ss = np.array([0, 5, 10, 14, 19], dtype=np.int32)
+    lay = np.array([0, 1, 2, 1, 0,   0, 1, 2, 1, 0,   0, 1, 1, 0,   0, 1, 2, 0, 1], dtype=np.int32)
+    ln = np.array([300.0, 500.0, 2000.0, 500.0 + 1e-7, 300.002,      # eligible
+                   300.0, 500.0, 2000.0, 500.1, 300.0,               # interior lengths 0.1 km apart
+                   300.0, 500.0, 500.0, 300.0,                       # even number of steps
+                   300.0, 500.0, 2000.0, 500.0, 300.0])              # layers not mirrored
+    got = np.empty((4, len(e)))
+    n_ok = hm.hm_p1e_mirror(e.ctypes.data_as(dp), len(e), ss.ctypes.data_as(ip), lay.ctypes.data_as(ip), ln.ctypes.data_as(dp), 4,
+                            lookup.ctypes.data_as(dp), len(lookup), 0.307, 0.0224, 7.5e-5, 5.2, got.ctypes.data_as(dp))
+    assert n_ok == 1
+    # the oracle takes stored (detector -> surface) lists: applied layer m = stored layer n-1-m, applied length m = stored length m
+    st_lay = np.concatenate([lay[a:b][::-1] for a, b in zip(ss[:-1], ss[1:])]) + 1
+    mp = O.OscPars(7.5e-5, math.asin(math.sqrt(0.307)), math.asin(math.sqrt(0.0224)))
+    ref = O.osc_prob_earth(e, mp, lookup, ss, st_lay, ln)
     assert np.max(np.abs(got - ref)) < 5e-12
 
 
