@@ -123,6 +123,7 @@ struct solarosc_handle {
     };
     std::vector<PipePlan> pipe_plans;
     bool use_pipe = true, pipe_all = false;
+    bool fine_all = false;      // SOLAROSC_FINE_ALL: the fine fold arrangement for independent points too (launch-shape experiments)
     int n_mirror = 0;           // paths that take the mirrored pair walk
     size_t smem_optin = 0;
 
@@ -246,6 +247,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     h->smem_optin = prop.sharedMemPerBlockOptin;
     h->use_pipe = std::getenv("SOLAROSC_NO_PIPE") == nullptr;   // A/B switches: the lock-step llh_kernel instead of pipe_kernel,
     h->pipe_all = std::getenv("SOLAROSC_PIPE_ALL") != nullptr;  // and pipe_kernel for independent points too
+    h->fine_all = std::getenv("SOLAROSC_FINE_ALL") != nullptr;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -810,7 +812,7 @@ bool launch_llh(solarosc_handle* h, const double* d_params, int n, int group, Ra
     if (h->fused_ok && h->use_fused && !h->gen && n_osc >= h->sm_count) {
         const RatesLaunch L = rates_launch(h, n, group, det_only);
         const int grid = std::min(n_osc, h->fused_grid);
-        if (mode == kModeLlh && group > 1 && h->fold_fine_ok) llh_kernel<kModeLlh, true><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
+        if (mode == kModeLlh && (group > 1 || h->fine_all) && h->fold_fine_ok) llh_kernel<kModeLlh, true><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         else if (mode == kModeLlh) llh_kernel<kModeLlh, false><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         else llh_kernel<kModeAsym, false><<<grid, kThreads, h->fused_smem, st>>>(h->T, L, d_params, O);
         CK(cudaGetLastError());
