@@ -426,6 +426,13 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
                     const std::vector<double> ra = to_row_major(x->resp_es_angular, D.n_cos, D.n_es, cm);
                     const std::vector<double> rb = to_row_major(x->resp_bg_angular, D.n_cos, D.n_es, cm);
                     std::vector<double> am((size_t)D.n_es * D.n_cos), bm(am.size());
+                    // The device applies the cut to the signal table only: the reference's BG.angular is zero in the bins the
+                    // cut removes by construction (response.jl:119-123), and the fold relies on that (it multiplies
+                    // BG/2 and the unmasked inclusive CC by the same table) -- anything else is refused here.
+                    for (int cs = 0; cs < D.n_cos; ++cs)
+                        for (int j = 0; j < D.n_es; ++j)
+                            REQUIRE(x->angular_mask[cs] != 0.0 || rb[(size_t)cs * D.n_es + j] == 0.0,
+                                    "resp_bg_angular must be zero in the cos-scatter bins angular_mask removes (response.jl:119-123)");
                     for (int cs = 0; cs < D.n_cos; ++cs)
                         for (int j = 0; j < D.n_es; ++j) {
                             am[(size_t)j * D.n_cos + cs] = x->angular_mask[cs] * ra[(size_t)cs * D.n_es + j];

@@ -99,7 +99,8 @@ typedef struct solarosc_detector_ext {
     const double *resp_cc_misid_nue;    /* [n_etrue][n_ereco_cc] responseMatrices.CC_misID_nue (inclusive == 2) */
     const double *resp_cc_misid_nuother;
     const double *resp_es_angular;      /* [n_cos][n_ereco_es]   responseMatrices.ES.angular (angular != 0) */
-    const double *resp_bg_angular;      /* [n_cos][n_ereco_es]   responseMatrices.BG.angular              */
+    const double *resp_bg_angular;      /* [n_cos][n_ereco_es]   responseMatrices.BG.angular; must be zero in the bins
+                                           angular_mask removes, as response.jl:119-123 builds it (checked at create) */
     const double *angular_mask;         /* [n_cos] 1.0 where the bin centre >= angular_cos_cut, else 0.0
                                            (propagation_reco.jl:98-105)                                  */
 } solarosc_detector_ext;

@@ -1,4 +1,5 @@
-"""Derived-mode quantities computed from batched rate arrays (host side, numpy).
+"""TEST INFRASTRUCTURE (checker, not product): derived-mode quantities computed from batched rate arrays (numpy).
+Only tests/ import this; the product computes the same sums on the device (`solarosc_eval_derived`).
 
 The reference's `RunMode: derived` replays a stored chain one sample at a time
 (`derive_variables_from_chain.jl:214-447`); with the engine the rates of a whole block of samples come

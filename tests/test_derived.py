@@ -1,7 +1,7 @@
 """Derived-mode reductions on the host against a literal per-sample loop (derive_variables_from_chain.jl:236-258)."""
 import numpy as np
 
-from dune_solaroscfitter_b200.derived import day_night_asymmetry, replay_block_sums, weighted_moments
+from oracle.derived_np import day_night_asymmetry, replay_block_sums, weighted_moments
 
 
 def test_asymmetry_matches_the_per_sample_loop():

@@ -171,7 +171,7 @@ def test_c4_night_only_cc_default_grid(tables, draw):
 # ---- C5: derived quantities over a stored chain ---------------------------------------------------------------------------
 def test_c5_day_night_asymmetry_and_moments(engine, tables, asimov, draw):
     """derive_variables_from_chain.jl:231-258,285-444: asymmetries from thresholded sums, weighted rate moments."""
-    from dune_solaroscfitter_b200.derived import day_night_asymmetry, weighted_moments
+    from oracle.derived_np import day_night_asymmetry, weighted_moments
     from oracle import oracle_c
     p = draw(tables, 64, seed=77)
     w = np.random.default_rng(1).integers(1, 5, 64).astype(float)
@@ -201,7 +201,7 @@ def test_c5_day_night_asymmetry_and_moments(engine, tables, asimov, draw):
 def test_c5_device_block_sums_match_the_replay_loop(engine, tables, asimov, draw):
     """solarosc_eval_derived against the replay loop (derive_variables_from_chain.jl:260-444) run in numpy on the
     oracle's rates and per-bin terms; 1100 samples span two internal chunks."""
-    from dune_solaroscfitter_b200.derived import replay_block_sums
+    from oracle.derived_np import replay_block_sums
     from oracle import oracle_c, oracle_np
     n = 1100
     p = draw(tables, n, seed=79)

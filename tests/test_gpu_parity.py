@@ -268,7 +268,10 @@ def test_parameter_corners(engine, coracle, tables):
     ref, rfl = coracle.eval_llh(p)
     assert np.array_equal(fl, rfl)
     assert np.max(np.abs(2 * got - 2 * ref)) < 1e-6
-    big = engine.eval_llh(np.tile(p, (12, 1)))                 # the fused kernel
+    big, bfl = engine.eval_llh(np.tile(p, (12, 1)), return_flags=True)   # the fused kernel, against the oracle as well
+    assert engine.last_timing()["fused"]
+    assert np.max(np.abs(2 * big.reshape(12, -1) - 2 * ref[None, :])) < 1e-6
+    assert np.array_equal(bfl.reshape(12, -1), np.tile(rfl, (12, 1)))
     assert np.max(np.abs(big.reshape(12, -1) - got[None, :])) < 1e-7
     p1e = engine.eval_p1e(p)
     _, rp1e = coracle.eval_oscprobs(p, want_p1e=True)
@@ -277,6 +280,33 @@ def test_parameter_corners(engine, coracle, tables):
     for k in ("ES_day", "ES_night", "CC_day", "CC_night"):
         scale = np.maximum(np.abs(rr[k]), 1e-9 * np.max(np.abs(rr[k])))
         assert np.max(np.abs(r[k] - rr[k]) / scale) < 1e-9, k
+
+
+@pytest.mark.parametrize("factor", [10.0, 100.0])
+def test_exposure_scaled_parity(tables, draw, factor):
+    """The rounding error of -2lnL grows with the counts per bin.  Exposure x 10 and x 100 (signal and background tables
+    scaled, Asimov data regenerated): the fused kernel against the oracle on prior draws.  The tolerance of the
+    specification, 1e-6 absolute, is stated for the nominal exposure; here the bound scales with the size of the sum,
+    1e-6 + 4e-15 |-2lnL| (a few hundred ulps of the largest partial sums), and the measured margin is printed."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    from oracle import oracle_c, oracle_np
+    t = dict(tables)
+    for k in ("unosc_es_nue_8b", "unosc_es_nuother_8b", "unosc_es_nue_hep", "unosc_es_nuother_hep", "unosc_cc_8b", "unosc_cc_hep",
+              "raw_bg_es", "raw_bg_cc"):
+        t[k] = factor * np.asarray(tables[k])
+    data = oracle_np.asimov_data(t)
+    p = draw(t, 1024, seed=77)
+    p[0] = t["truth"]
+    ref, _ = oracle_c.COracle(t, data).eval_llh(p)
+    with SolarOscEngine(t, data=data) as e:
+        got = e.eval_llh(p)
+        assert e.last_timing()["fused"]
+    err = np.abs(2 * got - 2 * ref)
+    bound = 1e-6 + 4e-15 * np.abs(2 * ref)
+    print(f"exposure x{factor:g}: max |d(-2lnL)| = {err.max():.2e} at -2lnL up to {np.abs(2 * ref).max():.2e}; "
+          f"largest err / bound = {np.max(err / bound):.2f}")
+    assert abs(got[0]) < 1e-6 * factor
+    assert np.all(err <= bound)
 
 
 def test_single_rank_communicator_gathers_the_same_values(tables, asimov, draw):
