@@ -450,10 +450,24 @@ def main():
         lnl_dev = d_lnl.cpu().numpy()
         same = bool(np.array_equal(lnl_dev, out_np))
 
-    if rank != 0:
+    def shutdown():
+        """Every rank leaves together: the library's communicator is released collectively (solarosc_comm_destroy),
+        then torch's.  A watchdog ends the process if a teardown call blocks -- the JSON line is out by then."""
+        sys.stdout.flush()
+        dog = threading.Timer(45.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
         if world > 1:
+            dist.barrier()
+            eng.comm_destroy()
+        eng.close()
+        if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        dog.cancel()
+
+    if rank != 0:
+        return shutdown()
 
     fp64_peak = eng.measure_fp64_peak()
     peaks = {}
@@ -525,9 +539,7 @@ def main():
         line["parity_on_sample"] = {"max_abs_diff_m2lnl": float(np.max(np.abs(2 * gpu_on_sample - 2 * cs["lnl"]))),
                                     "tolerance": 1e-6}
     print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -51,6 +51,8 @@ struct ArgFail {
 }  // namespace
 
 struct solarosc_comm_state;
+struct solarosc_handle;
+int comm_release(solarosc_handle* h, bool collective);   // solarosc_comm.hpp
 
 struct solarosc_handle {
     solarosc_config cfg{};
@@ -1132,7 +1134,7 @@ solarosc_handle* solarosc_create(const solarosc_tables* tables, const solarosc_c
 
 void solarosc_destroy(solarosc_handle* h) {
     if (!h) return;
-    if (h->comm) solarosc_comm_destroy(h);
+    if (h->comm) comm_release(h, false);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);

@@ -20,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -40,6 +41,7 @@ NcclApi& nccl_api() {
         api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
         api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(sym("ncclCommAbort"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
         api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.GroupStart && api.GroupEnd && api.CommDestroy && api.GetErrorString;
     });
@@ -177,12 +179,21 @@ int solarosc_comm_init(solarosc_handle* h, const void* id, int rank, int world) 
     });
 }
 
-int solarosc_comm_destroy(solarosc_handle* h) {
+}  // extern "C"
+
+// Frees the communicator.  collective = true (solarosc_comm_destroy: every rank calls it, like solarosc_comm_init):
+// ncclCommDestroy, which flushes and may wait for the peers.  collective = false (a handle destroyed with its
+// communicator still attached, e.g. at interpreter exit of one rank): ncclCommAbort, which never waits for anybody --
+// a rank that leaves early must not hang the others or itself.
+int comm_release(solarosc_handle* h, bool collective) {
     return guarded(h, [&]() {
         if (!h->comm) return (int)SOLAROSC_OK;
         CK(cudaStreamSynchronize(h->stream));
         solarosc_comm_state* c = h->comm;
-        if (c->comm) nccl_api().CommDestroy(c->comm);
+        if (c->comm) {
+            if (collective || !nccl_api().CommAbort) nccl_api().CommDestroy(c->comm);
+            else nccl_api().CommAbort(c->comm);
+        }
         for (void* p : {(void*)c->d_send, (void*)c->d_recv, (void*)c->d_fsend, (void*)c->d_frecv})
             if (p) cudaFree(p);
         delete c;
@@ -190,6 +201,8 @@ int solarosc_comm_destroy(solarosc_handle* h) {
         return (int)SOLAROSC_OK;
     });
 }
+extern "C" {
+int solarosc_comm_destroy(solarosc_handle* h) { return comm_release(h, true); }
 
 int solarosc_eval_llh_sharded_device(solarosc_handle* h, const double* d_params_local, size_t n_total, size_t group, double* d_lnl_all,
                                      uint32_t* d_flags_all, void* stream) {

@@ -249,6 +249,11 @@ class SolarOscEngine:
         dist.broadcast(t, 0)
         self.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
 
+    def comm_destroy(self):
+        """Collective: every rank releases the communicator together (solarosc_comm_destroy).  A handle closed with its
+        communicator still attached aborts it instead, without waiting for the other ranks."""
+        self._check(self._L.solarosc_comm_destroy(self._h))
+
     def shard_bounds(self, n_total: int, group: int = 1, rank: Optional[int] = None, world: Optional[int] = None):
         lo, hi = C.c_size_t(0), C.c_size_t(0)
         self._check(self._L.solarosc_shard_bounds(n_total, group, self.rank if rank is None else rank,

@@ -284,10 +284,13 @@ def test_parameter_corners(engine, coracle, tables):
 
 @pytest.mark.parametrize("factor", [10.0, 100.0])
 def test_exposure_scaled_parity(tables, draw, factor):
-    """The rounding error of -2lnL grows with the counts per bin.  Exposure x 10 and x 100 (signal and background tables
-    scaled, Asimov data regenerated): the fused kernel against the oracle on prior draws.  The tolerance of the
-    specification, 1e-6 absolute, is stated for the nominal exposure; here the bound scales with the size of the sum,
-    1e-6 + 4e-15 |-2lnL| (a few hundred ulps of the largest partial sums), and the measured margin is printed."""
+    """The rounding error of -2lnL grows with the counts per bin: the reference forms m (log m - log e) from two rounded
+    logarithms (likelihood_statistical.jl:19-23), so ANY two faithful double-precision evaluations -- Julia's log, glibc's,
+    the kernel's log_pos -- differ by about m ulp(log m) per bin, 3e-8 for the 1.8e7-count CC background bins of the
+    nominal exposure.  Exposure x 10 and x 100 (signal and background tables scaled, Asimov data regenerated), the fused
+    kernel against the oracle on prior draws: the error stays proportional to the exposure (measured 2.2e-7, 2.2e-6,
+    2.4e-5 at x 1, 10, 100), i.e. the 1e-6 tolerance of the nominal exposure scales with the counts, and stays far below
+    the worst case of the formula's own rounding, sum_bins 2 m ulp(log m)."""
     from dune_solaroscfitter_b200.engine import SolarOscEngine
     from oracle import oracle_c, oracle_np
     t = dict(tables)
@@ -302,11 +305,16 @@ def test_exposure_scaled_parity(tables, draw, factor):
         got = e.eval_llh(p)
         assert e.last_timing()["fused"]
     err = np.abs(2 * got - 2 * ref)
-    bound = 1e-6 + 4e-15 * np.abs(2 * ref)
-    print(f"exposure x{factor:g}: max |d(-2lnL)| = {err.max():.2e} at -2lnL up to {np.abs(2 * ref).max():.2e}; "
-          f"largest err / bound = {np.max(err / bound):.2f}")
+    ie, ic = int(t["index_es"]) - 1, int(t["index_cc"]) - 1
+    m = np.concatenate([np.ravel(data["ES_day"][ie:]), np.ravel(data["ES_night"][:, ie:]), np.ravel(data["CC_day"][ic:]),
+                        np.ravel(data["CC_night"][:, ic:])])
+    m = m[m > 0]
+    formula_noise = 2 * float(np.sum(2 * m * np.spacing(np.abs(np.log(m)))))     # -2lnL: two logarithms, one ulp each, every bin
+    print(f"exposure x{factor:g}: max |d(-2lnL)| = {err.max():.2e} (tolerance {1e-6 * factor:.0e}); worst case of the formula's own "
+          f"rounding {formula_noise:.1e}; -2lnL up to {np.abs(2 * ref).max():.2e}")
     assert abs(got[0]) < 1e-6 * factor
-    assert np.all(err <= bound)
+    assert err.max() <= 1e-6 * factor
+    assert err.max() < 0.5 * formula_noise
 
 
 def test_single_rank_communicator_gathers_the_same_values(tables, asimov, draw):
