@@ -1267,16 +1267,17 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
                           double* mom_es, double* mom_cc, double* bg_mom_es, double* bg_mom_cc, double* scalars) {
     return guarded(h, [&]() {
         REQUIRE(params && weights, "params and weights must not be NULL");
-        REQUIRE(!h->T.det[det < 0 || det >= h->T.n_det ? 0 : det].ang, "derived-mode reductions do not cover the angular ES reconstruction");
         REQUIRE(det >= 0 && det < h->T.n_det, "detector index out of range");
         check_data(h, det);
         const DevTables& T = h->T;
         const DevDetector& D = T.det[det];
         const int nZ = T.n_cosz, nE = h->n_es[det], nC = h->n_cc[det];
-        const int nel_es = (1 + nZ) * nE, nel_cc = (1 + nZ) * nC, n_elem = nel_es + nel_cc + nE + nC;
+        // angular ES reconstruction: the ES arrays carry the cos-scatter axis, [day: nCos][nE] then [night: nCos][nE][nZ]
+        const int nCos = D.ang ? D.n_cos : 1;
+        const int nel_es = (1 + nZ) * nE * nCos, nel_cc = (1 + nZ) * nC, n_elem = nel_es + nel_cc + nE + nC;
         const int n_slices = 32;
-        const size_t per = (size_t)(1 + nZ) * (nE + nC) + nE + nC;
-        const int step = std::max(1, std::min(h->chunk, 8192));
+        const size_t per = (size_t)nel_es + nel_cc + nE + nC + (D.ang ? nE : 0);
+        const int step = std::max(1, std::min(h->chunk, D.ang ? 2048 : 8192));
         const size_t fixed = (size_t)nel_es + nel_cc + (size_t)(n_slices + 1) * kDerivedQ * n_elem;
         h->ensure_scratch((per * step + 5 * (size_t)step + fixed) * sizeof(double));
         double* d_lref_es = h->d_scratch;
@@ -1297,12 +1298,13 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             CK(cudaMemcpyAsync(d_w, weights + b0, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             double* sp = d_rates;
             RatesOut O{};
-            O.es_day = sp; sp += (size_t)nb * nE;
-            O.es_night = sp; sp += (size_t)nb * nZ * nE;
+            O.es_day = sp; sp += (size_t)nb * nE * nCos;
+            O.es_night = sp; sp += (size_t)nb * nZ * nE * nCos;
             O.cc_day = sp; sp += (size_t)nb * nC;
             O.cc_night = sp; sp += (size_t)nb * nZ * nC;
             O.bg_es = sp; sp += (size_t)nb * nE;
-            O.bg_cc = sp;
+            O.bg_cc = sp; sp += (size_t)nb * nC;
+            double* d_es_day_sum = D.ang ? sp : nullptr;
             // rates with row-major night arrays whatever the handle's host layout is: the fused pipe_kernel when the chunk
             // fills the GPU (the probability block stays on the SM), else osc_kernel + rates_kernel
             if (!launch_pipe(h, h->d_params, nb, 1, kModeRates, det, O, h->stream, true)) {
@@ -1310,20 +1312,21 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
                 RatesLaunch L = rates_launch(h, nb, 1, det);
                 L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
                 const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
-                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GenLaunch{}, h->d_params, h->d_osc, O);
+                const GenLaunch GL{nE, 1, (long long)nE * nZ, nZ, 1};   // row-major [c][j] and [c][j][z]
+                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GL, h->d_params, h->d_osc, O);
                 else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, h->d_params, h->d_osc, O);
                 CK(cudaGetLastError());
                 ++h->launches;
             }
-            DerivedLaunch L{nb, n_slices, h->P, det, nZ, nE, nC, D.index_es - 1, D.index_cc - 1, b0 == 0 ? 1 : 0, T.earth_unc, T.n_layers};
+            DerivedLaunch L{nb, n_slices, h->P, det, nZ, nE, nC, D.index_es - 1, D.index_cc - 1, b0 == 0 ? 1 : 0, T.earth_unc, T.n_layers, nCos};
             DerivedIn I{O.es_day, O.es_night, O.cc_day, O.cc_night, O.bg_es, O.bg_cc, D.obs_es, D.obs_cc,
-                        lref_es ? d_lref_es : nullptr, lref_cc ? d_lref_cc : nullptr, h->d_params, d_w};
+                        lref_es ? d_lref_es : nullptr, lref_cc ? d_lref_cc : nullptr, h->d_params, d_w, D.ol_es_ang, d_es_day_sum};
             derived_sample_kernel<<<nb, 256, 0, h->stream>>>(L, I, d_ltot);
             derived_moment_kernel<<<dim3((n_elem + 255) / 256, n_slices), 256, 0, h->stream>>>(L, I, d_partial);
             CK(cudaGetLastError());
             h->launches += 2;
             CK(cudaMemcpyAsync(lt.data(), d_ltot, (size_t)4 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            if (es_day) CK(cudaMemcpyAsync(es_day + b0 * nE, O.es_day, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (es_day) CK(cudaMemcpyAsync(es_day + b0 * nE, D.ang ? d_es_day_sum : O.es_day, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             if (cc_day) CK(cudaMemcpyAsync(cc_day + b0 * nC, O.cc_day, (size_t)nb * nC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             for (int i = 0; i < nb; ++i) {   // derive...:343-348, 388-417, in sample order

@@ -1039,12 +1039,15 @@ struct DerivedLaunch {
     int nZ, nE, nC, idx_es, idx_cc;      // idx_*: 0-based first bin of the likelihood
     int first;                           // 1: partial sums start from zero, 0: they continue an earlier block
     int earth_unc, n_layers;
+    int nCos;                            // cos-scatter bins of the ES arrays (1: no angular reconstruction)
 };
 struct DerivedIn {
     const double *es_day, *es_night, *cc_day, *cc_night, *bg_es, *bg_cc;   // [n][..] device scratch
     const double *obs_es, *obs_cc;       // [1+nZ][nR]
     const double *lref_es, *lref_cc;     // [1+nZ][nR] or nullptr
     const double *params, *weights;
+    const double2* obs_es_ang;           // angular ES data (m, log m), [1 + nZ][nE][nCos]
+    double* es_day_sum;                  // angular: [n][nE] day rates summed over the cos-scatter bins (derive...:315-318)
 };
 constexpr int kDerivedQ = 6;
 
@@ -1068,6 +1071,26 @@ __device__ __forceinline__ void derived_element(int e, int nR, int nZ, int idx0,
     l = v - (lref ? lref[e] : 0.0);
 }
 
+// The same for element e of the angular ES arrays, laid out [day: nCos][nE] then [night: nCos][nE][nZ] (the reference's index
+// order, row-major): llh_ES_angle_perbin, likelihood_builder.jl:80-108; moments from the threshold bin on (derive...:288-296)
+__device__ __forceinline__ void derived_element_ang(int e, int nE, int nZ, int nCos, int idx0, size_t b, const double* day,
+                                                    const double* night, const double2* obs, const double* lref, bool oob,
+                                                    double& r, double& l, bool& above, bool& is_day) {
+    const int per_d = nCos * nE;
+    int c, j, row;
+    is_day = e < per_d;
+    if (is_day) { c = e / nE; j = e - c * nE; row = 0; r = day[b * per_d + e]; }
+    else {
+        const int x = e - per_d, cj = x / nZ;
+        c = cj / nE; j = cj - c * nE; row = 1 + (x - cj * nZ);
+        r = night[b * (size_t)per_d * nZ + x];
+    }
+    above = j >= idx0;
+    double v = (j >= idx0 && j < nE - 1) ? perbin_term(r, obs[((size_t)row * nE + j) * nCos + c].x) : 0.0;
+    if (oob) v = -INFINITY;
+    l = v - (lref ? lref[e] : 0.0);
+}
+
 // One CTA per sample: totals of the centred per-bin terms per (channel, day/night): out[b][4] = ES night, ES day,
 // CC night, CC day (derive...:388-417).
 __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch L, const DerivedIn I, double* __restrict__ ltot) {
@@ -1075,16 +1098,26 @@ __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch
     const size_t b = blockIdx.x;
     const bool oob = derived_oob(L, I.params + b * L.param_stride);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const int nel_es = (1 + L.nZ) * L.nE, nel_cc = (1 + L.nZ) * L.nC;
+    const int nel_es = (1 + L.nZ) * L.nE * L.nCos, nel_cc = (1 + L.nZ) * L.nC;
     for (int t = threadIdx.x; t < nel_es + nel_cc; t += blockDim.x) {
         const bool es = t < nel_es;
         const int e = es ? t : t - nel_es, nR = es ? L.nE : L.nC;
         double r, l;
-        bool above;
-        derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
-                        es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, oob, r, l, above);
-        acc[(es ? 0 : 2) + (e < nR ? 1 : 0)] += l;
+        bool above, is_day;
+        if (es && L.nCos > 1) derived_element_ang(e, L.nE, L.nZ, L.nCos, L.idx_es, b, I.es_day, I.es_night, I.obs_es_ang, I.lref_es, oob, r, l, above, is_day);
+        else {
+            derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
+                            es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, oob, r, l, above);
+            is_day = e < nR;
+        }
+        acc[(es ? 0 : 2) + (is_day ? 1 : 0)] += l;
     }
+    if (L.nCos > 1 && I.es_day_sum)   // the day spectrum per sample: sum over the cos-scatter bins, in bin order
+        for (int j = threadIdx.x; j < L.nE; j += blockDim.x) {
+            double sj = 0.0;
+            for (int c = 0; c < L.nCos; ++c) sj += I.es_day[b * (size_t)L.nCos * L.nE + c * L.nE + j];
+            I.es_day_sum[b * L.nE + j] = sj;
+        }
     for (int k = 0; k < 4; ++k) {
         const double s = block_sum(acc[k], red);
         if (threadIdx.x == 0) ltot[b * 4 + k] = s;
@@ -1094,7 +1127,7 @@ __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch
 // grid (elements / 256, n_slices): thread = one element, slice s walks samples s, s + n_slices, ... in order and adds
 // into partial[s][kDerivedQ][n_elem]; derived_finish_kernel adds the slices in order.  Deterministic.
 __global__ void __launch_bounds__(256) derived_moment_kernel(const DerivedLaunch L, const DerivedIn I, double* __restrict__ partial) {
-    const int nel_es = (1 + L.nZ) * L.nE, nel_cc = (1 + L.nZ) * L.nC, n_elem = nel_es + nel_cc + L.nE + L.nC;
+    const int nel_es = (1 + L.nZ) * L.nE * L.nCos, nel_cc = (1 + L.nZ) * L.nC, n_elem = nel_es + nel_cc + L.nE + L.nC;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_elem) return;
     double q[kDerivedQ];
@@ -1108,9 +1141,11 @@ __global__ void __launch_bounds__(256) derived_moment_kernel(const DerivedLaunch
             const bool es = t < nel_es;
             const int e = es ? t : t - nel_es, nR = es ? L.nE : L.nC;
             double r, l;
-            bool above;
-            derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
-                            es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, derived_oob(L, p), r, l, above);
+            bool above, is_day;
+            if (es && L.nCos > 1) derived_element_ang(e, L.nE, L.nZ, L.nCos, L.idx_es, b, I.es_day, I.es_night, I.obs_es_ang, I.lref_es,
+                                                      derived_oob(L, p), r, l, above, is_day);
+            else derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
+                                 es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, derived_oob(L, p), r, l, above);
             if (above) { q[0] += w * r; q[1] += w * (r * r); }
             q[2] += w * l; q[3] += w * (l * l); q[4] += w * (l * p[0]); q[5] += w * (l * p[2]);
         } else {

@@ -171,7 +171,9 @@ class SolarOscEngine:
         """Derived-mode block sums of derive_variables_from_chain.jl:260-444 for the (thinned-in) chain samples
         `params` with chain weights `weights`, reduced on the device.  `lref` holds the reference per-bin terms
         (keys ES_day, ES_night, CC_day, CC_night, e.g. eval_perbin at the truth).  Returns per-sample day rates and
-        per-bin-term totals, and the weighted sums, all row-major ([.., 1 + n_cosz, n_ereco], row 0 = day)."""
+        per-bin-term totals, and the weighted sums, all row-major ([.., 1 + n_cosz, n_ereco], row 0 = day).  With the
+        angular ES reconstruction ES_day is the day spectrum summed over the cos-scatter bins and the ES sums come as
+        mom_ES_day [6, n_cos, n_ereco] and mom_ES_night [6, n_cos, n_ereco, n_cosz] (lref in eval_perbin's shapes)."""
         p = self._params(params)
         n = len(p)
         w = np.ascontiguousarray(weights, dtype=np.float64)
@@ -179,6 +181,7 @@ class SolarOscEngine:
             raise ValueError("weights must have one entry per sample")
         nes, ncc = self.packed.n_ereco[det]
         nz = self.n_cosz
+        nc = self.packed.n_cos[det]
 
         def ref(ch, nr):
             if lref is None:
@@ -188,13 +191,26 @@ class SolarOscEngine:
                 night = night.T
             return np.ascontiguousarray(np.vstack([np.asarray(lref[ch + "_day"], dtype=np.float64).reshape(1, nr), night.reshape(nz, nr)]))
 
-        r_es, r_cc = ref("ES", nes), ref("CC", ncc)
+        def ref_ang():
+            """angular ES reference terms: [n_cos][n_ereco] day part, then [n_cos][n_ereco][n_cosz] night part"""
+            if lref is None:
+                return None
+            day, night = np.asarray(lref["ES_day"], dtype=np.float64), np.asarray(lref["ES_night"], dtype=np.float64)
+            if self.col_major:
+                day, night = day.T, night.transpose(2, 1, 0)
+            return np.ascontiguousarray(np.concatenate([day.reshape(nc * nes), night.reshape(nc * nes * nz)]))
+
+        r_es, r_cc = (ref_ang() if nc > 1 else ref("ES", nes)), ref("CC", ncc)
+        mom_es = np.empty((6, nc * nes * (1 + nz))) if nc > 1 else np.empty((6, 1 + nz, nes))
         out = dict(ES_day=np.empty((n, nes)), CC_day=np.empty((n, ncc)), ltot=np.empty((n, 4)),
-                   mom_ES=np.empty((6, 1 + nz, nes)), mom_CC=np.empty((6, 1 + nz, ncc)),
+                   mom_ES=mom_es, mom_CC=np.empty((6, 1 + nz, ncc)),
                    bg_mom_ES=np.empty((2, nes)), bg_mom_CC=np.empty((2, ncc)), scalars=np.empty(21))
         self._check(self._L.solarosc_eval_derived(self._h, det, _dp(p), n, _dp(w), _dp(r_es), _dp(r_cc), _dp(out["ES_day"]),
                                                   _dp(out["CC_day"]), _dp(out["ltot"]), _dp(out["mom_ES"]), _dp(out["mom_CC"]),
                                                   _dp(out["bg_mom_ES"]), _dp(out["bg_mom_CC"]), _dp(out["scalars"])))
+        if nc > 1:   # angular: the six ES blocks split into their day [n_cos, n_ereco] and night [n_cos, n_ereco, n_cosz] parts
+            out["mom_ES_day"] = mom_es[:, :nc * nes].reshape(6, nc, nes)
+            out["mom_ES_night"] = mom_es[:, nc * nes:].reshape(6, nc, nes, nz)
         return out
 
     def eval_oscprobs(self, params) -> Dict[str, np.ndarray]:

@@ -85,8 +85,8 @@ enum {
  * With angular != 0 every ES array gains the cos-scatter axis, in the reference's index order: ES day is
  * (n_cos, n_ereco_es), ES night (n_cos, n_ereco_es, n_cosz) -- row-major [c][j] and [c][j][z] when col_major == 0,
  * [j][c] and [z][j][c] when col_major == 1 -- for obs_es_* and for the es_day / es_night outputs of
- * solarosc_eval_rates and solarosc_eval_perbin.  solarosc_eval_derived does not cover the angular arrays and
- * solarosc_eval_llh_grad serves the exclusive, non-angular branch only: they return SOLAROSC_ERR_ARG otherwise.
+ * solarosc_eval_rates and solarosc_eval_perbin (solarosc_eval_derived: always the row-major form, see there).
+ * solarosc_eval_llh_grad serves the exclusive, non-angular branch only and returns SOLAROSC_ERR_ARG otherwise.
  */
 typedef struct solarosc_detector_ext {
     int32_t inclusive;                  /* 0 exclusive, 1 inclusive_analysis, 2 semi_inclusive_analysis  */
@@ -281,7 +281,11 @@ int solarosc_eval_asymmetry(solarosc_handle *h, int det, const double *params, s
  *             sum w l, sum w l^2, sum w l sin2_th12, sum w l dm2_21 with l the centred per-bin term
  *   bg_mom_es / bg_mom_cc  [2][n_ereco]: sum w (BG/2), sum w (BG/2)^2
  *   scalars   [21]: sum w, sum w th1, sum w th1^2, sum w th2, sum w th2^2 (th1 = sin2_th12, th2 = dm2_21), then for
- *             each group of ltot: sum w L, sum w L^2, sum w L th1, sum w L th2 */
+ *             each group of ltot: sum w L, sum w L^2, sum w L th1, sum w L th2
+ * With the angular ES reconstruction (derive...:239-258, 288-296, 315-318) the ES arrays carry the cos-scatter axis:
+ * lref_es and each of the six mom_es blocks hold n_cos n_ereco_es (1 + n_cosz) doubles, the day part [n_cos][n_ereco_es]
+ * followed by the night part [n_cos][n_ereco_es][n_cosz] (the reference's index order, row-major); es_day stays
+ * [n][n_ereco_es]: the day rates summed over the cos-scatter bins, which is what the reference lists per sample. */
 int solarosc_eval_derived(solarosc_handle *h, int det, const double *params, size_t n_points, const double *weights,
                           const double *lref_es, const double *lref_cc, double *es_day, double *cc_day, double *ltot,
                           double *mom_es, double *mom_cc, double *bg_mom_es, double *bg_mom_cc, double *scalars);

@@ -477,10 +477,45 @@ function derived_block_sums(params, weights::Vector{Float64}, lref; det::Int=0, 
     return (ES_day=ES_day, CC_day=CC_day, ltot=ltot, mom_ES=mom_es, mom_CC=mom_cc, bg_mom_ES=bg_es, bg_mom_CC=bg_cc, scalars=sc)
 end
 
+"""
+    derived_block_sums_angular(params, weights, lref; det, nz, nes, ncc, ncos)
+
+The same with the angular ES reconstruction (derive...:239-258, 288-296, 315-318).  The library lays the ES arrays out
+row-major as `[n_cos][n_E]` (day) followed by `[n_cos][n_E][n_cosz]` (night); read as Julia arrays these are
+`(n_E, n_cos)` and `(n_cosz, n_E, n_cos)`, so `permutedims` brings them to the reference's `(n_cos, n_E[, n_cosz])`.
+`ES_day` is `(n_E, B)`: the day spectrum summed over the cos-scatter bins (the reference's `es_total_above` is its
+`[index_ES:end]`).  Returns `mom_ES_day :: (n_cos, n_E, 6)` and `mom_ES_night :: (n_cos, n_E, n_cosz, 6)`.
+"""
+function derived_block_sums_angular(params, weights::Vector{Float64}, lref; det::Int=0, nz::Int, nes::Int, ncc::Int, ncos::Int)
+    M = pack_many(params); B = size(M, 2)
+    nd = ncos * nes; nn = nd * nz
+    # (n_cos, n_E) -> memory [c][j]: permutedims to (n_E, n_cos); (n_cos, n_E, n_cosz) -> memory [c][j][z]: (n_cosz, n_E, n_cos)
+    ref_es = vcat(vec(permutedims(lref.ES_day)), vec(permutedims(lref.ES_night, (3, 2, 1))))
+    ref_cc = hcat(lref.CC_day, permutedims(lref.CC_night))
+    ES_day = Array{Float64}(undef, nes, B); CC_day = Array{Float64}(undef, ncc, B); ltot = Array{Float64}(undef, 4, B)
+    mom_es = Array{Float64}(undef, nd + nn, 6); mom_cc = Array{Float64}(undef, ncc, 1 + nz, 6)
+    bg_es = Array{Float64}(undef, nes, 2); bg_cc = Array{Float64}(undef, ncc, 2); sc = Vector{Float64}(undef, 21)
+    GC.@preserve M weights ref_es ref_cc ES_day CC_day ltot mom_es mom_cc bg_es bg_cc sc begin
+        check(@ccall libb200.solarosc_eval_derived(handle[]::Handle, Cint(det)::Cint, pointer(M)::Ptr{Cdouble}, Csize_t(B)::Csize_t,
+            pointer(weights)::Ptr{Cdouble}, pointer(ref_es)::Ptr{Cdouble}, pointer(ref_cc)::Ptr{Cdouble},
+            pointer(ES_day)::Ptr{Cdouble}, pointer(CC_day)::Ptr{Cdouble}, pointer(ltot)::Ptr{Cdouble},
+            pointer(mom_es)::Ptr{Cdouble}, pointer(mom_cc)::Ptr{Cdouble}, pointer(bg_es)::Ptr{Cdouble},
+            pointer(bg_cc)::Ptr{Cdouble}, pointer(sc)::Ptr{Cdouble})::Cint)
+    end
+    day = Array{Float64}(undef, ncos, nes, 6); night = Array{Float64}(undef, ncos, nes, nz, 6)
+    for q in 1:6
+        day[:, :, q] = permutedims(reshape(view(mom_es, 1:nd, q), nes, ncos))
+        night[:, :, :, q] = permutedims(reshape(view(mom_es, nd+1:nd+nn, q), nz, nes, ncos), (3, 2, 1))
+    end
+    return (ES_day=ES_day, CC_day=CC_day, ltot=ltot, mom_ES_day=day, mom_ES_night=night, mom_CC=mom_cc,
+            bg_mom_ES=bg_es, bg_mom_CC=bg_cc, scalars=sc)
+end
+
 # ---- one Julia process per GPU: the library's own NCCL gather ----------------------------------------------------------
 """
     comm_unique_id() -> Vector{UInt8}      (rank 0; hand the 128 bytes to every rank, e.g. MPI.bcast)
     comm_init(id, rank, world)             (collective)
+    comm_destroy()                         (collective)
     total_llh_batch_sharded(params_local, n_total; group=1) -> Vector{Float64}   (lnL of ALL n_total points on every rank)
 
 Every rank passes the rows `shard_bounds(n_total, group, rank, world)` gives it; the per-point lnL vectors are
@@ -494,6 +529,9 @@ function comm_unique_id()
 end
 comm_init(id::Vector{UInt8}, rank::Int, world::Int) =
     GC.@preserve id check(@ccall libb200.solarosc_comm_init(handle[]::Handle, pointer(id)::Ptr{Cvoid}, Cint(rank)::Cint, Cint(world)::Cint)::Cint)
+# collective, like comm_init: every rank releases the communicator together, before the handle is destroyed (a handle destroyed
+# with its communicator attached aborts it without waiting for the other ranks)
+comm_destroy() = check(@ccall libb200.solarosc_comm_destroy(handle[]::Handle)::Cint)
 function shard_bounds(n_total::Int, group::Int, rank::Int, world::Int)
     lo = Ref{Csize_t}(0); hi = Ref{Csize_t}(0)
     st = @ccall libb200.solarosc_shard_bounds(Csize_t(n_total)::Csize_t, Csize_t(group)::Csize_t, Cint(rank)::Cint, Cint(world)::Cint,

@@ -74,3 +74,26 @@ def replay_block_sums(rates: dict, perbin: dict, lref: dict, params: np.ndarray,
                 out["ltot"][i, g] = tot
                 sc[5 + 4 * g: 9 + 4 * g] += np.array([w * tot, w * tot ** 2, w * tot * t1, w * tot * t2])
     return out
+
+
+def replay_block_sums_angular(rates: dict, perbin: dict, lref: dict, params: np.ndarray, weights: np.ndarray, index_es: int) -> dict:
+    """The ES part of the same loop with the angular reconstruction (derive_variables_from_chain.jl:239-258, 288-296,
+    315-318, 366-433): ES_day [B, n_cos, n], ES_night [B, n_cos, n, n_cosz] per sample.  Returns mom_ES_day
+    [6, n_cos, n], mom_ES_night [6, n_cos, n, n_cosz], ES_day [B, n] (the day spectrum summed over the cos-scatter bins)
+    and the ES columns of ltot [B, 2] (night, day)."""
+    B = len(weights)
+    k = index_es - 1
+    md, mn = np.zeros((6,) + rates["ES_day"].shape[1:]), np.zeros((6,) + rates["ES_night"].shape[1:])
+    es_day, ltot = np.zeros((B, rates["ES_day"].shape[2])), np.zeros((B, 2))
+    for i in range(B):
+        w, t1, t2 = float(weights[i]), float(params[i, 0]), float(params[i, 2])
+        rd, rn = rates["ES_day"][i], rates["ES_night"][i]
+        md[0][:, k:] += w * rd[:, k:]; md[1][:, k:] += w * rd[:, k:] ** 2
+        mn[0][:, k:, :] += w * rn[:, k:, :]; mn[1][:, k:, :] += w * rn[:, k:, :] ** 2
+        ld = perbin["ES_day"][i] - np.asarray(lref["ES_day"])
+        ln = perbin["ES_night"][i] - np.asarray(lref["ES_night"])
+        for m, l in ((md, ld), (mn, ln)):
+            m[2] += w * l; m[3] += w * l ** 2; m[4] += w * l * t1; m[5] += w * l * t2
+        es_day[i] = rd.sum(axis=0)
+        ltot[i] = ln.sum(), ld.sum()
+    return {"mom_ES_day": md, "mom_ES_night": mn, "ES_day": es_day, "ltot_ES": ltot}

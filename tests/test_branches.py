@@ -105,8 +105,6 @@ def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw)
         la = e.eval_llh(p)
         with pytest.raises(SolarOscError):             # the gradient entry serves the exclusive, non-angular analysis only
             e.eval_llh_grad(p)
-        with pytest.raises(SolarOscError):             # and the derived-mode sums do not cover the angular arrays
-            e.eval_derived(p, np.ones(len(p)))
     # the same tables and data as Julia lays them out (column-major: numpy views with reversed shapes)
     tj = dict(t)
     for k in ("resp_es_nue", "resp_es_nuother", "resp_cc", "resp_cc_incl", "resp_es_angular", "resp_bg_angular"):
@@ -194,3 +192,58 @@ def test_derived_sums_of_the_non_angular_branches(tables, branches, draw, incl):
     assert np.max(np.abs(got["mom_CC"][2][1:] - s1)) <= 1e-9 * max(1.0, np.max(np.abs(s1)))
     if incl == 1:
         assert np.all(got["mom_CC"][:2] == 0)                   # the CC arrays are zero in the inclusive analysis
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("incl,col_major", [(0, False), (1, False), (2, True)])
+def test_derived_sums_of_the_angular_arrays(tables, branches, draw, incl, col_major):
+    """solarosc_eval_derived with the angular ES reconstruction (derive_variables_from_chain.jl:239-258, 288-296, 315-318):
+    the device block sums over the (n_cos, n_ereco[, n_cosz]) arrays against the replay loop written out in numpy on the
+    engine's own per-sample rates and per-bin terms (which test_general_fold_matches_the_oracle pins to the oracle)."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    from oracle.derived_np import replay_block_sums_angular
+    t = branches(tables, incl, 1)
+    data = O.asimov_data(t)
+    n = 600                                                # three device chunks of the reduction (max_batch = 256 below)
+    p = draw(tables, n, seed=900 + incl)
+    p[7, 8] = 2.5                                          # one sample outside the earth-norm bounds: -Inf per-bin terms
+    w = np.random.default_rng(incl).integers(1, 4, n).astype(float)
+    tj, dj = t, data
+    if col_major:
+        tj = dict(t)
+        for k in ("resp_es_nue", "resp_es_nuother", "resp_cc", "resp_cc_incl", "resp_es_angular", "resp_bg_angular",
+                  "resp_cc_misid_nue", "resp_cc_misid_nuother"):
+            if k in t:
+                tj[k] = np.ascontiguousarray(np.asarray(t[k]).T)
+        dj = {k: np.ascontiguousarray(np.transpose(v)) for k, v in data.items()}
+    with SolarOscEngine(t, data=data) as e0:               # row-major twin: per-sample arrays for the replay loop
+        rates, pb = e0.eval_rates(p), e0.eval_perbin(p)
+        lref = {k: v[0] for k, v in e0.eval_perbin(np.asarray(t["truth"], dtype=float)[None, :]).items()}
+    with SolarOscEngine(tj, data=dj, col_major=col_major, max_batch=256) as e:
+        lr = lref if not col_major else {k: np.ascontiguousarray(np.transpose(v)) for k, v in lref.items()}
+        got = e.eval_derived(p, w, lr)
+        a_es, _ = e.eval_asymmetry(p[:64])
+    ok = np.ones(n, dtype=bool); ok[7] = False
+    sub = lambda d: {k: v[ok] for k, v in d.items()}     # noqa: E731  (the -Inf sample poisons the sums by design: checked apart)
+    ref = replay_block_sums_angular(rates, pb, lref, p, w, int(t["index_es"]))
+    assert np.array_equal(got["ES_day"], ref["ES_day"]) or np.max(np.abs(got["ES_day"] - ref["ES_day"])) <= 1e-12 * np.max(ref["ES_day"])
+    assert np.all(np.isneginf(got["ltot"][7, :2])) and np.allclose(got["ltot"][ok, :2], ref["ltot_ES"][ok], rtol=1e-11, atol=1e-9)
+    for q in (0, 1):                                       # rate moments: every sample counts, zero below the threshold
+        for key in ("mom_ES_day", "mom_ES_night"):
+            r = ref[key][q]
+            assert np.max(np.abs(got[key][q] - r)) <= 1e-12 * np.max(np.abs(r)), (key, q)
+    k = int(t["index_es"]) - 1
+    assert np.all(got["mom_ES_day"][0][:, :k] == 0) and np.all(got["mom_ES_night"][1][:, :k, :] == 0)
+    assert np.all(np.isinf(got["mom_ES_day"][2]) | np.isnan(got["mom_ES_day"][2]))     # the out-of-bounds sample, as in the reference
+    with SolarOscEngine(t, data=data) as e1:               # the same block without that sample: finite centred sums
+        g1 = e1.eval_derived(p[ok], w[ok], lref)
+    r1 = replay_block_sums_angular(sub(rates), sub(pb), lref, p[ok], w[ok], int(t["index_es"]))
+    for q in range(2, 6):
+        for key in ("mom_ES_day", "mom_ES_night"):
+            r = r1[key][q]
+            assert np.max(np.abs(g1[key][q] - r)) <= 1e-11 * max(1.0, np.max(np.abs(r))), (key, q)
+    # asymmetry of the angular arrays (derive...:239-246): sums over every cos-scatter bin from the threshold on
+    bg = rates["BG_ES_tot"][:64, k:].sum(axis=1)
+    dd = rates["ES_day"][:64][:, :, k:].sum(axis=(1, 2)) - 0.5 * bg
+    nn = rates["ES_night"][:64][:, :, k:, :].sum(axis=(1, 2, 3)) - 0.5 * bg
+    assert np.max(np.abs(a_es - 2 * (dd - nn) / (dd + nn))) < 1e-10
