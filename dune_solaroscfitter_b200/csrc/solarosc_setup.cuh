@@ -21,7 +21,11 @@
 
 namespace solarosc_setup {
 
-// numpy.linspace(lo, hi, n + 1) / Julia range(lo, stop=hi, length=n+1): lo + i*step, last point exactly hi
+// numpy.linspace(lo, hi, n + 1): lo + i*step in plain double, last point exactly hi.  Julia's
+// range(lo, stop=hi, length=n+1) is a twice-precision StepRangeLen whose elements are correctly rounded and can differ
+// from these by an ulp: bin indices are bit-exact against this repository's numpy builders (and the shipped CC MC, whose
+// values sit far from the edges), parity of the edges with Julia is unverified -- solarosc_setup_bin_index also takes
+// explicit edge arrays, which is how a Julia host passes its own.
 inline std::vector<double> linspace(double lo, double hi, int n_intervals) {
     std::vector<double> e(n_intervals + 1);
     const double step = (hi - lo) / n_intervals;
