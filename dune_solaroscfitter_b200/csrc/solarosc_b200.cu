@@ -93,6 +93,8 @@ struct solarosc_handle {
     bool small_fused = false;
     uint32_t* h_flags2[2]{};
     double* d_scratch = nullptr; // rate / per-bin / p1e outputs, grown on demand
+    double* h_dstage[2]{};       // pinned staging of the derived-mode per-sample outputs
+    size_t h_dstage_bytes = 0;
     double* d_gradws = nullptr;  // gradient path, two slots: probabilities, d lnL / d P, gradient rows
     size_t gradws_bytes = 0;
     size_t grad_smem = 0, adj_smem = 0;
@@ -1146,6 +1148,7 @@ void solarosc_destroy(solarosc_handle* h) {
         if (h->h_grad_pin[i]) cudaFreeHost(h->h_grad_pin[i]);
     for (int i = 0; i < 2; ++i) {
         if (h->h_lnl2[i]) cudaFreeHost(h->h_lnl2[i]);
+        if (h->h_dstage[i]) cudaFreeHost(h->h_dstage[i]);
         if (h->h_flags2[i]) cudaFreeHost(h->h_flags2[i]);
     }
     for (int i = 0; i < 2; ++i) {
@@ -1276,25 +1279,66 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
         const int nCos = D.ang ? D.n_cos : 1;
         const int nel_es = (1 + nZ) * nE * nCos, nel_cc = (1 + nZ) * nC, n_elem = nel_es + nel_cc + nE + nC;
         const int n_slices = 32;
-        const size_t per = (size_t)nel_es + nel_cc + nE + nC + (D.ang ? nE : 0);
+        const size_t per = (size_t)2 * (nel_es + nel_cc) + nE + nC + (D.ang ? nE : 0);   // rates, centred per-bin terms, backgrounds
         const int step = std::max(1, std::min(h->chunk, D.ang ? 2048 : 8192));
         const size_t fixed = (size_t)nel_es + nel_cc + (size_t)(n_slices + 1) * kDerivedQ * n_elem;
-        h->ensure_scratch((per * step + 5 * (size_t)step + fixed) * sizeof(double));
+        const size_t slot_doubles = per * step + 5 * (size_t)step;
+        h->ensure_scratch((2 * slot_doubles + fixed) * sizeof(double));
         double* d_lref_es = h->d_scratch;
         double* d_lref_cc = d_lref_es + nel_es;
         double* d_partial = d_lref_cc + nel_cc;
         double* d_out = d_partial + (size_t)n_slices * kDerivedQ * n_elem;
-        double* d_w = d_out + (size_t)kDerivedQ * n_elem;
-        double* d_ltot = d_w + step;
-        double* d_rates = d_ltot + 4 * (size_t)step;
+        double* d_slots = d_out + (size_t)kDerivedQ * n_elem;
+        // per-sample outputs come back through two pinned staging slots: [step][4 + nE + nC]
+        const size_t stage_bytes = (size_t)step * (4 + nE + nC) * sizeof(double);
+        if (stage_bytes > h->h_dstage_bytes) {
+            for (int i = 0; i < 2; ++i) {
+                if (h->h_dstage[i]) cudaFreeHost(h->h_dstage[i]);
+                h->h_dstage[i] = nullptr;
+                CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_dstage[i]), stage_bytes));
+            }
+            h->h_dstage_bytes = stage_bytes;
+        }
         if (lref_es) CK(cudaMemcpyAsync(d_lref_es, lref_es, nel_es * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         if (lref_cc) CK(cudaMemcpyAsync(d_lref_cc, lref_cc, nel_cc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        std::vector<double> acc(21, 0.0), lt((size_t)4 * step);
+        std::vector<double> acc(21, 0.0);
         h->launches = 0;
         if (n == 0) CK(cudaMemsetAsync(d_out, 0, (size_t)kDerivedQ * n_elem * sizeof(double), h->stream));
-        for (size_t b0 = 0; b0 < n; b0 += step) {
-            const int nb = (int)std::min<size_t>(step, n - b0);
-            CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        // Chunks are pipelined over two slots: the kernels of chunk c + 1 run while the per-sample outputs of chunk c travel
+        // to the pinned staging (s_out) and the host adds chunk c - 1's scalar sums, sample by sample, in sample order.
+        struct Slot { size_t b0; int nb; };
+        Slot sl[2];
+        auto collect = [&](int slot) {
+            const Slot& q = sl[slot];
+            CK(cudaEventSynchronize(h->ev_out[slot]));
+            const double* lt = h->h_dstage[slot];
+            const double* ed = lt + (size_t)4 * step;
+            const double* cd = ed + (size_t)step * nE;
+            if (es_day) std::memcpy(es_day + q.b0 * nE, ed, (size_t)q.nb * nE * sizeof(double));
+            if (cc_day) std::memcpy(cc_day + q.b0 * nC, cd, (size_t)q.nb * nC * sizeof(double));
+            for (int i = 0; i < q.nb; ++i) {   // derive...:343-348, 388-417, in sample order
+                const double w = weights[q.b0 + i], t1 = params[(q.b0 + i) * h->P + 0], t2 = params[(q.b0 + i) * h->P + 2];
+                acc[0] += w; acc[1] += w * t1; acc[2] += w * (t1 * t1); acc[3] += w * t2; acc[4] += w * (t2 * t2);
+                for (int g = 0; g < 4; ++g) {
+                    const double l = lt[(size_t)4 * i + g];
+                    acc[5 + 4 * g + 0] += w * l; acc[5 + 4 * g + 1] += w * (l * l);
+                    acc[5 + 4 * g + 2] += w * (l * t1); acc[5 + 4 * g + 3] += w * (l * t2);
+                }
+            }
+            if (ltot) std::memcpy(ltot + 4 * q.b0, lt, (size_t)4 * q.nb * sizeof(double));
+        };
+        size_t c = 0;
+        for (size_t b0 = 0; b0 < n; b0 += step, ++c) {
+            const int nb = (int)std::min<size_t>(step, n - b0), slot = (int)(c & 1);
+            if (c >= 2) {
+                collect(slot);                                                    // chunk c - 2 has left this slot's staging
+                CK(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));           // ... and its device scratch
+            }
+            double* d_w = d_slots + (size_t)slot * slot_doubles;
+            double* d_ltot = d_w + step;
+            double* d_rates = d_ltot + 4 * (size_t)step;
+            double* d_par = h->d_params2[slot];
+            CK(cudaMemcpyAsync(d_par, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             CK(cudaMemcpyAsync(d_w, weights + b0, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             double* sp = d_rates;
             RatesOut O{};
@@ -1305,41 +1349,38 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
             O.bg_es = sp; sp += (size_t)nb * nE;
             O.bg_cc = sp; sp += (size_t)nb * nC;
             double* d_es_day_sum = D.ang ? sp : nullptr;
+            if (D.ang) sp += (size_t)nb * nE;
+            double* d_lbuf = sp;
             // rates with row-major night arrays whatever the handle's host layout is: the fused pipe_kernel when the chunk
             // fills the GPU (the probability block stays on the SM), else osc_kernel + rates_kernel
-            if (!launch_pipe(h, h->d_params, nb, 1, kModeRates, det, O, h->stream, true)) {
-                launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
+            if (!launch_pipe(h, d_par, nb, 1, kModeRates, det, O, h->stream, true)) {
+                launch_osc(h, d_par, nb, 1, nullptr, h->stream);
                 RatesLaunch L = rates_launch(h, nb, 1, det);
                 L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
                 const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
                 const GenLaunch GL{nE, 1, (long long)nE * nZ, nZ, 1};   // row-major [c][j] and [c][j][z]
-                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GL, h->d_params, h->d_osc, O);
-                else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, h->d_params, h->d_osc, O);
+                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GL, d_par, h->d_osc, O);
+                else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, d_par, h->d_osc, O);
                 CK(cudaGetLastError());
                 ++h->launches;
             }
             DerivedLaunch L{nb, n_slices, h->P, det, nZ, nE, nC, D.index_es - 1, D.index_cc - 1, b0 == 0 ? 1 : 0, T.earth_unc, T.n_layers, nCos};
             DerivedIn I{O.es_day, O.es_night, O.cc_day, O.cc_night, O.bg_es, O.bg_cc, D.obs_es, D.obs_cc,
-                        lref_es ? d_lref_es : nullptr, lref_cc ? d_lref_cc : nullptr, h->d_params, d_w, D.ol_es_ang, d_es_day_sum};
+                        lref_es ? d_lref_es : nullptr, lref_cc ? d_lref_cc : nullptr, d_par, d_w, D.ol_es_ang, d_es_day_sum, d_lbuf};
             derived_sample_kernel<<<nb, 256, 0, h->stream>>>(L, I, d_ltot);
             derived_moment_kernel<<<dim3((n_elem + 255) / 256, n_slices), 256, 0, h->stream>>>(L, I, d_partial);
             CK(cudaGetLastError());
             h->launches += 2;
-            CK(cudaMemcpyAsync(lt.data(), d_ltot, (size_t)4 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            if (es_day) CK(cudaMemcpyAsync(es_day + b0 * nE, D.ang ? d_es_day_sum : O.es_day, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            if (cc_day) CK(cudaMemcpyAsync(cc_day + b0 * nC, O.cc_day, (size_t)nb * nC * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            for (int i = 0; i < nb; ++i) {   // derive...:343-348, 388-417, in sample order
-                const double w = weights[b0 + i], t1 = params[(b0 + i) * h->P + 0], t2 = params[(b0 + i) * h->P + 2];
-                acc[0] += w; acc[1] += w * t1; acc[2] += w * (t1 * t1); acc[3] += w * t2; acc[4] += w * (t2 * t2);
-                for (int g = 0; g < 4; ++g) {
-                    const double l = lt[(size_t)4 * i + g];
-                    acc[5 + 4 * g + 0] += w * l; acc[5 + 4 * g + 1] += w * (l * l);
-                    acc[5 + 4 * g + 2] += w * (l * t1); acc[5 + 4 * g + 3] += w * (l * t2);
-                }
-            }
-            if (ltot) std::memcpy(ltot + 4 * b0, lt.data(), (size_t)4 * nb * sizeof(double));
+            CK(cudaEventRecord(h->ev_done[slot], h->stream));
+            CK(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+            double* st = h->h_dstage[slot];
+            CK(cudaMemcpyAsync(st, d_ltot, (size_t)4 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+            if (es_day) CK(cudaMemcpyAsync(st + (size_t)4 * step, D.ang ? d_es_day_sum : O.es_day, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+            if (cc_day) CK(cudaMemcpyAsync(st + (size_t)4 * step + (size_t)step * nE, O.cc_day, (size_t)nb * nC * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+            CK(cudaEventRecord(h->ev_out[slot], h->s_out));
+            sl[slot] = Slot{b0, nb};
         }
+        for (size_t k = c >= 2 ? c - 2 : 0; k < c; ++k) collect((int)(k & 1));
         if (n > 0) {
             derived_finish_kernel<<<(kDerivedQ * n_elem + 255) / 256, 256, 0, h->stream>>>(n_slices, n_elem, d_partial, d_out);
             CK(cudaGetLastError());

@@ -38,11 +38,16 @@ __host__ __device__ inline size_t grad_scratch_doubles(int n_etrue, int max_erec
     const size_t kt4 = 4 * fold_kt(n_etrue), nt8 = 8 * ((max_ereco + 7) / 8);
     return 4 * kt4 + 4 * nt8 + (size_t)kWarps * (kGradShared > kGradBg ? kGradShared : kGradBg) + kGradShared + kGradBg + 8;
 }
+// Three tile pairs (P, Pbar, G) of exactly 1 + n_cosz rows each -- the last 8-row MMA tile of a pair reads past its rows into
+// whatever follows, which only feeds output rows the epilogues drop (an MMA output row depends on the same A row only) --
+// so that two CTAs fit one SM (111 kB each in the default binning).  `tail` pads the odd case where what follows the last
+// tile is shorter than that overrun.
 __host__ __device__ inline size_t grad_smem_bytes(int n_etrue, int n_cosz, int max_ereco) {
-    const int rows = fold_rows(1 + n_cosz);
-    return sizeof(double) * (2 * fold_p_doubles(n_etrue, 1 + n_cosz) + (size_t)2 * rows * fold_ld(8 * ((max_ereco + 7) / 8)) +
-                             grad_scratch_doubles(n_etrue, max_ereco));
+    const int nrow = 1 + n_cosz, ldp = fold_ldp(n_etrue), ldg = fold_ld(8 * ((max_ereco + 7) / 8));
+    const size_t over = (size_t)(fold_rows(nrow) - nrow) * (ldg > ldp ? ldg : ldp), after = grad_scratch_doubles(n_etrue, max_ereco);
+    return sizeof(double) * ((size_t)4 * nrow * ldp + (size_t)2 * nrow * ldg + after + (over > after ? over - after : 0));
 }
+constexpr int kMCgrad = 4;   // row tiles the gradient folds keep in flight (4 accumulators each: the register budget of two CTAs per SM)
 
 __device__ __forceinline__ double rcp_pos(double x) {
     double r;
@@ -97,21 +102,21 @@ __device__ __forceinline__ void block_reduce(const double (&v)[N], double* red /
 // One CTA per parameter point.  osc holds the oscillation probabilities [n_points][2 proc][1 + n_cosz][n_etrue] as
 // osc_kernel writes them; pbar_out receives d lnL / d P in the same layout (adjoint_kernel's input).  The gradient row
 // is zeroed, then the flux, cross-section and background columns are written; the oscillation columns stay zero here.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ params, const double* __restrict__ osc,
             double* __restrict__ pbar_out, double* __restrict__ out_lnl, double* __restrict__ out_grad /* [n_points][n_params] */,
             uint32_t* __restrict__ out_flags) {
     extern __shared__ __align__(16) double smem[];
     __shared__ uint32_t redf[kWarps];
-    const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ, ldp = fold_ldp(nT), rows = fold_rows(nrow);
+    const int nT = T.n_etrue, nZ = T.n_cosz, nrow = 1 + nZ, ldp = fold_ldp(nT), rows = nrow;   // no padding rows (grad_smem_bytes)
     const int kt = fold_kt(nT), mt = (nrow + 7) / 8;
     const int ntm = (L.max_ereco + 7) / 8, ldg = fold_ld(8 * ntm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, fg = lane >> 2, ft = lane & 3;
     double* p8s = smem;                                       // probabilities, A operand of the forward fold
     double* phs = p8s + (size_t)rows * ldp;
-    double* q8s = p8s + fold_p_doubles(nT, nrow);             // d lnL / d P, same layout
+    double* q8s = phs + (size_t)rows * ldp;                   // d lnL / d P, same layout
     double* qhs = q8s + (size_t)rows * ldp;
-    double* g_es = q8s + fold_p_doubles(nT, nrow);            // d lnL / d x, A operand of the backward fold
+    double* g_es = qhs + (size_t)rows * ldp;                  // d lnL / d x, A operand of the backward fold
     double* g_cc = g_es + (size_t)rows * ldg;
     double* scr = g_cc + (size_t)rows * ldg;
     double* shape = scr;                  // [4 kt] s_i = norm exp(tilt l + curv l^2)
@@ -211,11 +216,11 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
             const double2* ol = is_es ? D.ol_es : D.ol_cc;
             double* gt = (is_es ? g_es : g_cc) + n0 + 2 * ft;
             const size_t bstep = (size_t)4 * ldb;
-            for (int m0 = 0; m0 < mt; m0 += kMC) {
-                double x8[kMC][2], xh[kMC][2];
-                uint32_t a8[kMC];
+            for (int m0 = 0; m0 < mt; m0 += kMCgrad) {
+                double x8[kMCgrad][2], xh[kMCgrad][2];
+                uint32_t a8[kMCgrad];
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) {
+                for (int c = 0; c < kMCgrad; ++c) {
                     x8[c][0] = c80; x8[c][1] = c81; xh[c][0] = ch0; xh[c][1] = ch1;
                     a8[c] = smem_addr(p8s + fg * ldp + ft) + (uint32_t)min(m0 + c, mt - 1) * tile_bytes;
                 }
@@ -226,13 +231,13 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     const double b8v = __ldg(q8) * s, bhv = __ldg(qh) * s;
                     q8 += bstep; qh += bstep;
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
+                    for (int c = 0; c < kMCgrad; ++c) {
                         dmma_8x8x4(x8[c][0], x8[c][1], lds_f64(a8[c] + 32u * ks), b8v);
                         dmma_8x8x4(xh[c][0], xh[c][1], lds_f64(a8[c] + dproc + 32u * ks), bhv);
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) {
+                for (int c = 0; c < kMCgrad; ++c) {
                     const int row = 8 * (m0 + c) + fg;
                     const bool vr = m0 + c < mt && row < nrow;
                     const double w = (row == 0) ? 1.0 : T.wz[min(row, nrow - 1) - 1];
@@ -249,7 +254,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                             sh[1] = fma(g, x8[c][hh], sh[1]);
                             sh[2] = fma(g, xh[c][hh], sh[2]);
                         }
-                        if (m0 + c < mt) gt[(size_t)row * ldg + hh] = g;
+                        if (vr) gt[(size_t)row * ldg + hh] = g;      // (rows past the tile pair belong to the next array)
                     }
                 }
             }
@@ -288,11 +293,11 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
             const int n0 = 8 * task;
             const int icol = min(n0 + fg, kp - 1);                  // row of the fold matrices this lane's B element sits in
             const int i0 = n0 + 2 * ft;                             // this lane's two true-energy bins
-            for (int m0 = 0; m0 < mt; m0 += kMC) {
-                double a8v[kMC][2], ahv[kMC][2];
-                uint32_t ga[kMC];
+            for (int m0 = 0; m0 < mt; m0 += kMCgrad) {
+                double a8v[kMCgrad][2], ahv[kMCgrad][2];
+                uint32_t ga[kMCgrad];
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) {
+                for (int c = 0; c < kMCgrad; ++c) {
                     a8v[c][0] = a8v[c][1] = ahv[c][0] = ahv[c][1] = 0.0;
                     ga[c] = (uint32_t)min(m0 + c, mt - 1) * gtile_bytes + (uint32_t)(fg * ldg + ft) * 8u;
                 }
@@ -303,7 +308,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     for (int ks = 0; ks < 2 * btc; ++ks) {
                         const double b8v = __ldg(q8 + 4 * ks), bhv = __ldg(qh + 4 * ks);
 #pragma unroll
-                        for (int c = 0; c < kMC; ++c) {
+                        for (int c = 0; c < kMCgrad; ++c) {
                             const double gv = lds_f64(gbase + ga[c] + 32u * ks);
                             dmma_8x8x4(a8v[c][0], a8v[c][1], gv, b8v);
                             dmma_8x8x4(ahv[c][0], ahv[c][1], gv, bhv);
@@ -312,7 +317,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     // cross-section shape: H_i = sum_rows F8 P8 (G_CC B8^T) + Fh Ph (G_CC Bh^T)
                     double h0 = 0.0, h1 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
+                    for (int c = 0; c < kMCgrad; ++c) {
                         const int row = 8 * (m0 + c) + fg;
                         if (m0 + c < mt && row < nrow) {
                             if (i0 < nT) h0 += f8 * p8s[row * ldp + i0] * a8v[c][0] + fh * phs[row * ldp + i0] * ahv[c][0];
@@ -330,7 +335,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     }
                     const double s0 = shape[min(i0, kp - 1)], s1 = shape[min(i0 + 1, kp - 1)];
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) { a8v[c][0] *= s0; a8v[c][1] *= s1; ahv[c][0] *= s0; ahv[c][1] *= s1; }
+                    for (int c = 0; c < kMCgrad; ++c) { a8v[c][0] *= s0; a8v[c][1] *= s1; ahv[c][0] *= s0; ahv[c][1] *= s1; }
                 }
                 if (D.es_mode) {
                     const double* q8 = D.a8_thr + (size_t)icol * 8 * bte + ft;
@@ -339,7 +344,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     for (int ks = 0; ks < 2 * bte; ++ks) {
                         const double b8v = __ldg(q8 + 4 * ks), bhv = __ldg(qh + 4 * ks);
 #pragma unroll
-                        for (int c = 0; c < kMC; ++c) {
+                        for (int c = 0; c < kMCgrad; ++c) {
                             const double gv = lds_f64(gbase + ga[c] + 32u * ks);
                             dmma_8x8x4(a8v[c][0], a8v[c][1], gv, b8v);
                             dmma_8x8x4(ahv[c][0], ahv[c][1], gv, bhv);
@@ -347,7 +352,7 @@ grad_kernel(const DevTables T, const GradLaunch L, const double* __restrict__ pa
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) {
+                for (int c = 0; c < kMCgrad; ++c) {
                     const int row = 8 * (m0 + c) + fg;
                     if (m0 + c < mt && row < nrow) {
                         if (i0 < nT) { q8s[row * ldp + i0] += f8 * a8v[c][0]; qhs[row * ldp + i0] += fh * ahv[c][0]; }

@@ -1048,6 +1048,8 @@ struct DerivedIn {
     const double *params, *weights;
     const double2* obs_es_ang;           // angular ES data (m, log m), [1 + nZ][nE][nCos]
     double* es_day_sum;                  // angular: [n][nE] day rates summed over the cos-scatter bins (derive...:315-318)
+    double* lbuf;                        // [n][nel_es + nel_cc] centred per-bin terms: written by derived_sample_kernel, read by
+                                         // derived_moment_kernel (one logarithm per element and sample instead of two)
 };
 constexpr int kDerivedQ = 6;
 
@@ -1062,10 +1064,12 @@ __device__ __forceinline__ bool derived_oob(const DerivedLaunch& L, const double
 }
 // rate and centred per-bin term of element e of a channel for sample b
 __device__ __forceinline__ void derived_element(int e, int nR, int nZ, int idx0, size_t b, const double* day, const double* night,
-                                                const double* obs, const double* lref, bool oob, double& r, double& l, bool& above) {
+                                                const double* obs, const double* lref, bool oob, double& r, double& l, bool& above,
+                                                const double* lpre = nullptr) {
     const int row = e / nR, j = e - row * nR;
     r = row == 0 ? day[b * nR + j] : night[(b * nZ + (row - 1)) * nR + j];
     above = j >= idx0;
+    if (lpre) { l = *lpre; return; }
     double v = (j >= idx0 && j < nR - 1) ? perbin_term(r, obs[e]) : 0.0;
     if (oob) v = -INFINITY;              // make_perbin_likelihood, likelihood_builder.jl:271-282
     l = v - (lref ? lref[e] : 0.0);
@@ -1075,7 +1079,7 @@ __device__ __forceinline__ void derived_element(int e, int nR, int nZ, int idx0,
 // order, row-major): llh_ES_angle_perbin, likelihood_builder.jl:80-108; moments from the threshold bin on (derive...:288-296)
 __device__ __forceinline__ void derived_element_ang(int e, int nE, int nZ, int nCos, int idx0, size_t b, const double* day,
                                                     const double* night, const double2* obs, const double* lref, bool oob,
-                                                    double& r, double& l, bool& above, bool& is_day) {
+                                                    double& r, double& l, bool& above, bool& is_day, const double* lpre = nullptr) {
     const int per_d = nCos * nE;
     int c, j, row;
     is_day = e < per_d;
@@ -1086,6 +1090,7 @@ __device__ __forceinline__ void derived_element_ang(int e, int nE, int nZ, int n
         r = night[b * (size_t)per_d * nZ + x];
     }
     above = j >= idx0;
+    if (lpre) { l = *lpre; return; }
     double v = (j >= idx0 && j < nE - 1) ? perbin_term(r, obs[((size_t)row * nE + j) * nCos + c].x) : 0.0;
     if (oob) v = -INFINITY;
     l = v - (lref ? lref[e] : 0.0);
@@ -1094,7 +1099,6 @@ __device__ __forceinline__ void derived_element_ang(int e, int nE, int nZ, int n
 // One CTA per sample: totals of the centred per-bin terms per (channel, day/night): out[b][4] = ES night, ES day,
 // CC night, CC day (derive...:388-417).
 __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch L, const DerivedIn I, double* __restrict__ ltot) {
-    __shared__ double red[8];
     const size_t b = blockIdx.x;
     const bool oob = derived_oob(L, I.params + b * L.param_stride);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1111,6 +1115,7 @@ __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch
             is_day = e < nR;
         }
         acc[(es ? 0 : 2) + (is_day ? 1 : 0)] += l;
+        if (I.lbuf) I.lbuf[b * (size_t)(nel_es + nel_cc) + t] = l;
     }
     if (L.nCos > 1 && I.es_day_sum)   // the day spectrum per sample: sum over the cos-scatter bins, in bin order
         for (int j = threadIdx.x; j < L.nE; j += blockDim.x) {
@@ -1118,9 +1123,18 @@ __global__ void __launch_bounds__(256) derived_sample_kernel(const DerivedLaunch
             for (int c = 0; c < L.nCos; ++c) sj += I.es_day[b * (size_t)L.nCos * L.nE + c * L.nE + j];
             I.es_day_sum[b * L.nE + j] = sj;
         }
+    // the four totals in one pass: warp sums to shared memory, one barrier, warps added in order (deterministic)
+    __shared__ double red4[4][8];
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double s = block_sum(acc[k], red);
-        if (threadIdx.x == 0) ltot[b * 4 + k] = s;
+        const double s = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) red4[k][threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red4[threadIdx.x][w];
+        ltot[b * 4 + threadIdx.x] = s;
     }
 }
 
@@ -1142,10 +1156,12 @@ __global__ void __launch_bounds__(256) derived_moment_kernel(const DerivedLaunch
             const int e = es ? t : t - nel_es, nR = es ? L.nE : L.nC;
             double r, l;
             bool above, is_day;
+            const double* lpre = I.lbuf ? I.lbuf + b * (size_t)(nel_es + nel_cc) + t : nullptr;
+            const bool oob = lpre ? false : derived_oob(L, p);
             if (es && L.nCos > 1) derived_element_ang(e, L.nE, L.nZ, L.nCos, L.idx_es, b, I.es_day, I.es_night, I.obs_es_ang, I.lref_es,
-                                                      derived_oob(L, p), r, l, above, is_day);
+                                                      oob, r, l, above, is_day, lpre);
             else derived_element(e, nR, L.nZ, es ? L.idx_es : L.idx_cc, b, es ? I.es_day : I.cc_day, es ? I.es_night : I.cc_night,
-                                 es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, derived_oob(L, p), r, l, above);
+                                 es ? I.obs_es : I.obs_cc, es ? I.lref_es : I.lref_cc, oob, r, l, above, lpre);
             if (above) { q[0] += w * r; q[1] += w * (r * r); }
             q[2] += w * l; q[3] += w * (l * l); q[4] += w * (l * p[0]); q[5] += w * (l * p[2]);
         } else {
