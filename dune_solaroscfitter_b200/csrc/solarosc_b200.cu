@@ -80,7 +80,8 @@ struct solarosc_handle {
     // workspaces
     double* d_params2[2]{};      // double-buffered parameter chunks
     double* d_params = nullptr;  // == d_params2[0]
-    double* d_osc = nullptr;
+    double* d_osc = nullptr;     // stage-separated probabilities [chunk][2][1 + n_cosz][n_etrue]; use osc()
+    size_t osc_doubles = 0;
     double* d_lnl2[2]{};
     uint32_t* d_flags2[2]{};
     double* h_lnl2[2]{};         // pinned staging of the results of one chunk, double-buffered
@@ -145,6 +146,11 @@ struct solarosc_handle {
         return d;
     }
     double* upload_vec(const std::vector<double>& v) { return upload(v.data(), v.size()); }
+    // workspace of the stage-separated path (1 GiB at the default max_batch): allocated when a call first takes that path
+    double* osc() {
+        if (!d_osc) d_osc = dalloc<double>(osc_doubles);
+        return d_osc;
+    }
     cudaEvent_t next_tev() {
         if (tev_used == tev.size()) {
             cudaEvent_t e;
@@ -540,7 +546,7 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
         CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags2[i]), (size_t)h->chunk * sizeof(uint32_t)));
     }
     h->d_params = h->d_params2[0];
-    h->d_osc = h->dalloc<double>((size_t)h->chunk * osc_pt);
+    h->osc_doubles = (size_t)h->chunk * osc_pt;   // allocated on first use (osc()): the fused kernels never need it
     const size_t rs = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
     // A binning whose probability tile does not fit one SM's shared memory (e.g. the 1000 x 1000 zenith x
     // energy convergence sweep) can still use the oscillation-stage entry points; the fold needs the tile.
@@ -640,7 +646,7 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     const bool seg = sm + h->seg_bytes <= std::min<size_t>(h->osc_smem_limit, 110 * 1024);
     if (seg) sm += h->seg_bytes;
     OscLaunch L{n_osc, n_chunks, cb, h->P, point_step, seg ? 1 : 0};
-    osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, d_out ? d_out : h->d_osc, d_p1e);
+    osc_kernel<<<n_osc * n_chunks, kThreads, sm, st>>>(T, L, d_params, d_out ? d_out : h->osc(), d_p1e);
     CK(cudaGetLastError());
     ++h->launches;
 }
@@ -669,11 +675,11 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
         const TiledLaunch TL{h->tiled_rows, h->tiled_chunks, h->d_tiled_part, h->d_tiled_flags};
         const int grid = n * h->tiled_chunks;
         if (mode == kModeLlh) {
-            rates_tiled_kernel<kModeLlh><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
+            rates_tiled_kernel<kModeLlh><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->osc(), O);
             tiled_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(TL, n, O.lnl, O.flags);
             ++h->launches;
-        } else if (mode == kModeRates) rates_tiled_kernel<kModeRates><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
-        else rates_tiled_kernel<kModePerbin><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->d_osc, O);
+        } else if (mode == kModeRates) rates_tiled_kernel<kModeRates><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->osc(), O);
+        else rates_tiled_kernel<kModePerbin><<<grid, kThreads, h->tiled_smem, st>>>(T, L, TL, d_params, h->osc(), O);
         CK(cudaGetLastError());
         ++h->launches;
         return;
@@ -684,18 +690,18 @@ void launch_rates(solarosc_handle* h, const double* d_params, int n, int group, 
         const bool cm = h->cfg.col_major != 0;
         const long long nC = h->n_cos[d], nE = h->n_es[d], nZ = T.n_cosz;
         const GenLaunch GL = cm ? GenLaunch{1, nC, 1, nC, nC * nE} : GenLaunch{nE, 1, nE * nZ, nZ, 1};
-        if (mode == kModeLlh) gen_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
-        else if (mode == kModeRates) gen_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
-        else if (mode == kModePerbin) gen_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
-        else gen_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->d_osc, O);
+        if (mode == kModeLlh) gen_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->osc(), O);
+        else if (mode == kModeRates) gen_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->osc(), O);
+        else if (mode == kModePerbin) gen_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->osc(), O);
+        else gen_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, GL, d_params, h->osc(), O);
         CK(cudaGetLastError());
         ++h->launches;
         return;
     }
-    if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
-    else if (mode == kModeAsym) rates_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
-    else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
-    else rates_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, d_params, h->d_osc, O);
+    if (mode == kModeLlh) rates_kernel<kModeLlh><<<n, kThreads, sm, st>>>(T, L, d_params, h->osc(), O);
+    else if (mode == kModeAsym) rates_kernel<kModeAsym><<<n, kThreads, sm, st>>>(T, L, d_params, h->osc(), O);
+    else if (mode == kModeRates) rates_kernel<kModeRates><<<n, kThreads, sm, st>>>(T, L, d_params, h->osc(), O);
+    else rates_kernel<kModePerbin><<<n, kThreads, sm, st>>>(T, L, d_params, h->osc(), O);
     CK(cudaGetLastError());
     ++h->launches;
 }
@@ -876,6 +882,7 @@ int eval_llh_small(solarosc_handle* h, const double* params, size_t n, size_t gr
         if (h->small_graph) { cudaGraphExecDestroy(h->small_graph); h->small_graph = nullptr; }
         cudaGraph_t g = nullptr;
         if (n / group >= (size_t)h->sm_count) pipe_plan(h, kModeLlh, (int)group, -1);   // uploads its tables: not inside a capture
+        else h->osc();                                                                  // (nor the workspace allocation)
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         try {
             CK(cudaMemcpyAsync(h->d_params2[0], h->h_params_pin, n * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1359,8 +1366,8 @@ int solarosc_eval_derived(solarosc_handle* h, int det, const double* params, siz
                 L.s_row_es = nE; L.s_j_es = 1; L.s_row_cc = nC; L.s_j_cc = 1;
                 const size_t sm = rates_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
                 const GenLaunch GL{nE, 1, (long long)nE * nZ, nZ, 1};   // row-major [c][j] and [c][j][z]
-                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GL, d_par, h->d_osc, O);
-                else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, d_par, h->d_osc, O);
+                if (h->gen) gen_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, GL, d_par, h->osc(), O);
+                else rates_kernel<kModeRates><<<nb, kThreads, sm, h->stream>>>(T, L, d_par, h->osc(), O);
                 CK(cudaGetLastError());
                 ++h->launches;
             }
@@ -1416,7 +1423,7 @@ int solarosc_eval_cc_incl_spectrum(solarosc_handle* h, int det, const double* pa
             const int nb = (int)std::min<size_t>(h->chunk, n - b0);
             CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
-            cc_incl_spectrum_kernel<<<nb, kThreads, 2 * h->T.n_etrue * sizeof(double), h->stream>>>(h->T, det, h->P, h->d_params, h->d_osc, h->d_scratch);
+            cc_incl_spectrum_kernel<<<nb, kThreads, 2 * h->T.n_etrue * sizeof(double), h->stream>>>(h->T, det, h->P, h->d_params, h->osc(), h->d_scratch);
             CK(cudaGetLastError());
             ++h->launches;
             CK(cudaMemcpyAsync(out + b0 * nE, h->d_scratch, (size_t)nb * nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1438,7 +1445,7 @@ int solarosc_eval_oscprobs(solarosc_handle* h, const double* params, size_t n, d
             const int nb = (int)std::min<size_t>(h->chunk, n - b0);
             CK(cudaMemcpyAsync(h->d_params, params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             launch_osc(h, h->d_params, nb, 1, nullptr, h->stream);
-            CK(cudaMemcpyAsync(host.data(), h->d_osc, (size_t)nb * 2 * nrow * nT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(host.data(), h->osc(), (size_t)nb * 2 * nrow * nT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             for (int i = 0; i < nb; ++i) {
                 const double* s8 = host.data() + (size_t)i * 2 * nrow * nT;
