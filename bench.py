@@ -479,7 +479,7 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu capture (bytes per point x points per launch)
     traffic, pts_per_launch = None, n * args.steps / max(1, launches)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_llh_kernel_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_llh_kernel_traffic.json")))
         traffic = tr["dram_bytes_per_point"] * pts_per_launch
     except Exception:
         pass
@@ -489,7 +489,7 @@ def main():
         ach = n * (FLOP_OSC + FLOP_RATES) / osc_s * 1e-12
         roofline = {"bound": "fp64", "kernel": "llh_kernel (fused K1-K5)", "achieved": ach, "peak": fp64_peak,
                     "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                    "traffic_note": "DRAM bytes per launch: ncu dram__bytes_read+write per point (profiles/r01_llh_kernel_traffic.json) "
+                    "traffic_note": "DRAM bytes per launch: ncu dram__bytes_read+write per point (profiles/r02_llh_kernel_traffic.json) "
                                     f"x {pts_per_launch:.0f} points per launch; algorithmic bytes are 164 per point",
                     "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                     "ms_per_step": ms_osc / args.steps, "share_of_step": 1.0,

@@ -1004,8 +1004,10 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     const int n_osc = L.n_points / L.group;
     for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
         const double* po = params + (size_t)g * L.group * L.param_stride;
-        // point g*group's fold vectors ride along with the first eigen table (no barrier needed in between: the
-        // scratch was last read before the closing barrier of the previous fold)
+        // point g*group's fold vectors ride along with the first eigen table.  The likelihood fold ends with a barrier
+        // behind its last read of the scratch; the asymmetry fold does not (thread 0 still sums the backgrounds), so a
+        // persistent grid (SOLAROSC_LLH_GRID) needs one here before the scratch is rewritten.
+        if (MODE != kModeLlh && g != (int)blockIdx.x) __syncthreads();
         const int d0 = L.det_only >= 0 ? L.det_only : 0;
         fold_vectors<MODE>(T, T.det[d0], po, (size_t)g * L.group, scr, O);
         for (int i0 = 0; i0 < nT; i0 += cbs) {
