@@ -6,7 +6,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS ?= -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-O3 -Xptxas -v
 PKG       := dune_solaroscfitter_b200
 SRC       := $(PKG)/csrc/solarosc_b200.cu
-HDR       := $(PKG)/csrc/solarosc_device.cuh $(PKG)/csrc/solarosc_kernels.cuh $(PKG)/csrc/solarosc_pipe.cuh $(PKG)/csrc/solarosc_grad.cuh $(PKG)/csrc/solarosc_adjoint.cuh $(PKG)/csrc/solarosc_adjoint_math.cuh $(PKG)/csrc/solarosc_general.cuh $(PKG)/csrc/solarosc_setup.cuh $(PKG)/csrc/solarosc_batcher.hpp $(PKG)/csrc/solarosc_comm.hpp include/solarosc_b200.h
+HDR       := $(PKG)/csrc/solarosc_device.cuh $(PKG)/csrc/solarosc_kernels.cuh $(PKG)/csrc/solarosc_pipe.cuh $(PKG)/csrc/solarosc_grad.cuh $(PKG)/csrc/solarosc_adjoint.cuh $(PKG)/csrc/solarosc_adjoint_math.cuh $(PKG)/csrc/solarosc_general.cuh $(PKG)/csrc/solarosc_gengrad.cuh $(PKG)/csrc/solarosc_setup.cuh $(PKG)/csrc/solarosc_batcher.hpp $(PKG)/csrc/solarosc_comm.hpp include/solarosc_b200.h
 LIB       := $(PKG)/libsolarosc_b200.so
 
 all: $(LIB) oracle

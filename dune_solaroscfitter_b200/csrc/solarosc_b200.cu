@@ -18,6 +18,7 @@
 #include "solarosc_adjoint.cuh"
 #include "solarosc_pipe.cuh"
 #include "solarosc_general.cuh"
+#include "solarosc_gengrad.cuh"
 #include "solarosc_setup.cuh"
 
 using namespace solarosc;
@@ -98,7 +99,7 @@ struct solarosc_handle {
     size_t h_dstage_bytes = 0;
     double* d_gradws = nullptr;  // gradient path, two slots: probabilities, d lnL / d P, gradient rows
     size_t gradws_bytes = 0;
-    size_t grad_smem = 0, adj_smem = 0;
+    size_t grad_smem = 0, adj_smem = 0, gengrad_smem = 0;
     double* h_grad_pin[2]{};     // pinned staging of the gradient rows of one chunk
     bool grad_ok = false;
     size_t scratch_bytes = 0;
@@ -579,7 +580,9 @@ void build(solarosc_handle* h, const solarosc_tables* t, const solarosc_config* 
     CK(cudaFuncSetAttribute(osc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->osc_smem_limit));
     h->grad_smem = grad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
     h->adj_smem = sizeof(double) * (adj_smem_doubles(T.n_ltbl, T.n_e, seg_smem_doubles(T.n_seg, T.n_paths, T.n_cosz)) + 2);
-    h->grad_ok = h->grad_smem <= prop.sharedMemPerBlockOptin && h->adj_smem <= prop.sharedMemPerBlockOptin;
+    h->gengrad_smem = gengrad_smem_bytes(T.n_etrue, T.n_cosz, h->max_ereco);
+    h->grad_ok = (h->gen ? h->gengrad_smem : h->grad_smem) <= prop.sharedMemPerBlockOptin && h->adj_smem <= prop.sharedMemPerBlockOptin;
+    if (h->grad_ok && h->gen) CK(cudaFuncSetAttribute(gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gengrad_smem));
     if (h->grad_ok) {
         CK(cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_smem));
         CK(cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->adj_smem));
@@ -1042,7 +1045,6 @@ int eval_arrays_host(solarosc_handle* h, int det, int mode, const double* params
 int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, double* out_lnl, double* out_grad, uint32_t* flags) {
     REQUIRE(params && out_lnl && out_grad, "params, out_lnl and out_grad must not be NULL");
     REQUIRE(h->grad_ok, "binning too large for the gradient kernels' shared-memory tiles");
-    REQUIRE(!h->gen, "the gradient entry serves the exclusive, non-angular analysis only");
     REQUIRE(!h->T.night_only, "the gradient entry does not offer night_only");
     check_data(h, -1);
     const DevTables& T = h->T;
@@ -1081,7 +1083,10 @@ int eval_llh_grad_host(solarosc_handle* h, const double* params, size_t n, doubl
         CK(cudaMemcpyAsync(h->d_params2[slot], params + b0 * h->P, (size_t)nb * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         launch_osc(h, h->d_params2[slot], nb, 1, nullptr, h->stream, d_osc);
         GradLaunch G{nb, h->P, h->max_ereco};
-        grad_kernel<<<nb, kThreads, h->grad_smem, h->stream>>>(T, G, h->d_params2[slot], d_osc, d_pbar, h->d_lnl2[slot], d_grad, h->d_flags2[slot]);
+        if (h->gen)   // a handle with an inclusive / semi-inclusive / angular detector: the general fold's reverse mode
+            gen_grad_kernel<<<nb, kThreads, h->gengrad_smem, h->stream>>>(T, G, h->d_params2[slot], d_osc, d_pbar, h->d_lnl2[slot], d_grad, h->d_flags2[slot]);
+        else
+            grad_kernel<<<nb, kThreads, h->grad_smem, h->stream>>>(T, G, h->d_params2[slot], d_osc, d_pbar, h->d_lnl2[slot], d_grad, h->d_flags2[slot]);
         AdjLaunch A{nb, h->P};
         adjoint_kernel<<<nb, kThreads, h->adj_smem, h->stream>>>(T, A, h->d_params2[slot], d_pbar, d_grad, h->d_flags2[slot]);
         CK(cudaGetLastError());

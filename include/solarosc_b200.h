@@ -86,7 +86,7 @@ enum {
  * (n_cos, n_ereco_es), ES night (n_cos, n_ereco_es, n_cosz) -- row-major [c][j] and [c][j][z] when col_major == 0,
  * [j][c] and [z][j][c] when col_major == 1 -- for obs_es_* and for the es_day / es_night outputs of
  * solarosc_eval_rates and solarosc_eval_perbin (solarosc_eval_derived: always the row-major form, see there).
- * solarosc_eval_llh_grad serves the exclusive, non-angular branch only and returns SOLAROSC_ERR_ARG otherwise.
+ * solarosc_eval_llh_grad serves every branch (gen_grad_kernel for handles with such a detector).
  */
 typedef struct solarosc_detector_ext {
     int32_t inclusive;                  /* 0 exclusive, 1 inclusive_analysis, 2 semi_inclusive_analysis  */
@@ -240,7 +240,8 @@ int solarosc_eval_llh_sharded_device(solarosc_handle *h, const double *d_params_
  * tests/test_adjoint_highprec.py).  sin2_th12 and sin2_th13 are clamped to [0, 1] by the reference
  * (propagation_osc.jl:30-36): their columns are 0 outside the open interval.  Columns the likelihood does not depend
  * on ({det}_ES_bg_norm_2.., which the reference never reads) get 0, as does every column of a point whose earth
- * norms are out of bounds (lnL = -Inf).  Exclusive, non-angular analysis. */
+ * norms are out of bounds (lnL = -Inf).  Every analysis branch (exclusive, inclusive, semi-inclusive, each with or
+ * without the angular ES reconstruction; a handle may mix them); night_only handles are refused. */
 int solarosc_eval_llh_grad(solarosc_handle *h, const double *params, size_t n_points, double *out_lnl,
                            double *out_grad, uint32_t *out_flags);
 

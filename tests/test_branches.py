@@ -96,15 +96,13 @@ def test_general_fold_matches_the_oracle(tables, branches, draw, incl, ang):
 
 @pytest.mark.gpu
 def test_general_fold_julia_layout_and_unsupported_calls(tables, branches, draw):
-    from dune_solaroscfitter_b200.engine import SolarOscEngine, SolarOscError
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
     t = branches(tables, 1, 1)
     data = O.asimov_data(t)
     p = draw(tables, 3, seed=77)
     with SolarOscEngine(t, data=data) as e:
         a = e.eval_rates(p)
         la = e.eval_llh(p)
-        with pytest.raises(SolarOscError):             # the gradient entry serves the exclusive, non-angular analysis only
-            e.eval_llh_grad(p)
     # the same tables and data as Julia lays them out (column-major: numpy views with reversed shapes)
     tj = dict(t)
     for k in ("resp_es_nue", "resp_es_nuother", "resp_cc", "resp_cc_incl", "resp_es_angular", "resp_bg_angular"):
@@ -247,3 +245,52 @@ def test_derived_sums_of_the_angular_arrays(tables, branches, draw, incl, col_ma
     dd = rates["ES_day"][:64][:, :, k:].sum(axis=(1, 2)) - 0.5 * bg
     nn = rates["ES_night"][:64][:, :, k:, :].sum(axis=(1, 2, 3)) - 0.5 * bg
     assert np.max(np.abs(a_es - 2 * (dd - nn) / (dd + nn))) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("incl,ang", BRANCHES)
+def test_gradient_of_the_branches(tables, branches, draw, incl, ang):
+    """solarosc_eval_llh_grad on the inclusive / semi-inclusive / angular branches (gen_grad_kernel + adjoint_kernel):
+    the value is eval_llh's, every column agrees with 4th-order central differences of the engine's own lnL (which
+    test_general_fold_matches_the_oracle pins to the oracle) along the coordinate axes and along random directions."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    t = branches(tables, incl, ang)
+    data = O.asimov_data(t)
+    p = draw(tables, 12, seed=700 + 10 * incl + ang)
+    p[0] = t["truth"]; p[0, 0] += 0.01; p[0, 3] *= 1.02
+    p[11, 9] = 2.3                                         # out of the earth-norm bounds: -Inf, zero gradient row
+    with SolarOscEngine(t, data=data) as e:
+        lnl, grad = e.eval_llh_grad(p)
+        ref = e.eval_llh(p)
+        assert np.isneginf(lnl[11]) and np.all(grad[11] == 0)
+        ok = np.arange(11)
+        assert np.max(np.abs(2 * lnl[ok] - 2 * ref[ok])) < 1e-6
+        assert np.all(np.isfinite(grad[ok]))
+        P = p.shape[1]
+        for k in range(P):
+            if k in (15, 16):                              # ES background norms 2 and 3 do not enter (every ES component uses norm_1)
+                assert np.all(grad[ok, k] == 0)
+                continue
+            if k == 2:
+                h = 1e-4 * np.abs(p[ok, k])                 # dm2_21: the phases make lnL oscillate in it
+            elif k in (0, 1) or 8 <= k < 14:
+                h = np.full(len(ok), 1e-3)                  # mixing angles, earth norms
+            elif k >= 14:
+                h = 1e-3 * np.abs(p[ok, k])                 # background norms (~1e-5): lnL is strongly curved in them
+            else:
+                h = 1e-3 * np.maximum(np.abs(p[ok, k]), 1e-2)   # fluxes, cross-section norm / tilt / curvature
+            f = []
+            for m in (-2, -1, 1, 2):
+                q = p[ok].copy(); q[:, k] += m * h
+                f.append(e.eval_llh(q))
+            fd = (f[0] - 8 * f[1] + 8 * f[2] - f[3]) / (12 * h)
+            tol = (2e-4 if k == 2 else 2e-5) * np.abs(grad[ok, k]) + 2e-6 / h
+            assert np.all(np.abs(fd - grad[ok, k]) <= tol), (k, fd, grad[ok, k])
+        rng = np.random.default_rng(incl + 3 * ang)
+        v = rng.normal(size=p[ok].shape) * (np.abs(p[ok]) * 2e-4 + 1e-12)
+        v[:, 14:] *= 1e-2
+        f = [e.eval_llh(p[ok] + m * v) for m in (-2, -1, 1, 2)]
+        fd = (f[0] - 8 * f[1] + 8 * f[2] - f[3]) / 12
+        pred = np.sum(grad[ok] * v, axis=1)
+        # (the differences carry the rounding noise of up to 38 k Poisson terms per point with the angular reconstruction)
+        assert np.max(np.abs(fd - pred) / np.maximum(np.abs(pred), 1e-2)) < (1e-4 if ang else 5e-6)

@@ -80,6 +80,16 @@ def test_exclusive_and_angular_detectors_in_one_handle(tables, asimov, branches,
     with SolarOscEngine(tables, detectors=[tables, tv], data=[asimov, dv]) as e:
         got = e.eval_llh(p)
         r0, r1 = e.eval_rates(p, det=0), e.eval_rates(p, det=1)
+        # value + gradient of the mixed handle (gen_grad_kernel walks both detectors): the value, and grad . v against
+        # 4th-order differences of the handle's own lnL along random directions over all 24 columns
+        lnl, grad = e.eval_llh_grad(p)
+        assert np.max(np.abs(2 * lnl - 2 * got)) < 1e-6 and grad.shape == p.shape
+        v = np.random.default_rng(4).normal(size=p.shape) * (np.abs(p) * 2e-4 + 1e-12)
+        v[:, 14:] *= 1e-2
+        f = [e.eval_llh(p + m * v) for m in (-2, -1, 1, 2)]
+        fd = (f[0] - 8 * f[1] + 8 * f[2] - f[3]) / 12
+        pred = np.sum(grad * v, axis=1)
+        assert np.max(np.abs(fd - pred) / np.maximum(np.abs(pred), 1e-2)) < 1e-4
     assert r0["ES_night"].shape == (4, 50, 30) and r1["ES_night"].shape == (4, 25, 30, 50)
     for i in range(len(p)):
         p0 = p[i, :19]
