@@ -23,6 +23,12 @@ namespace solarosc {
 #ifndef SOLAROSC_OSC_THREADS
 #define SOLAROSC_OSC_THREADS 256
 #endif
+#ifndef SOLAROSC_MIRROR_UNROLL_PAR
+#define SOLAROSC_MIRROR_UNROLL_PAR 1   // both fine energies of a coarse bin get their own copy of the pair walk: +1.4 % (profiles/r02_notes.md)
+#endif
+#ifndef SOLAROSC_EIG_NODUP
+#define SOLAROSC_EIG_NODUP 1   // every eigen entry computed once (entries 2t, 2t + 1 per thread): +0.4 %
+#endif
 #ifndef SOLAROSC_OSC_MINBLOCKS
 #define SOLAROSC_OSC_MINBLOCKS 2
 #endif
@@ -57,8 +63,14 @@ constexpr int kPhaseSlots = 16, kPhaseCtas = 4096, kPhaseFirst = 8192;
 __device__ long long g_phase[kPhaseSlots * kPhaseCtas];
 #define SOLAROSC_PH(i)                                                                                   \
     do {                                                                                                 \
-        if (threadIdx.x == 0 && blockIdx.x >= kPhaseFirst && blockIdx.x < kPhaseFirst + kPhaseCtas)      \
+        if (threadIdx.x == 0 && blockIdx.x >= kPhaseFirst && blockIdx.x < kPhaseFirst + kPhaseCtas) {    \
             g_phase[(blockIdx.x - kPhaseFirst) * kPhaseSlots + (i)] = clock64();                         \
+            if ((i) == 0) {   /* slot 15: the SM this CTA runs on (pairs co-resident CTAs: tools/phase_pairs.py) */ \
+                unsigned smid_;                                                                          \
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                                       \
+                g_phase[(blockIdx.x - kPhaseFirst) * kPhaseSlots + 15] = smid_;                          \
+            }                                                                                            \
+        }                                                                                                \
     } while (0)
 #else
 #define SOLAROSC_PH(i)
@@ -222,7 +234,11 @@ __device__ __forceinline__ void path_p1e_pair(const SegTables& G, const double* 
     } else if (sg.pad != 0) {
         const double lenx = load_seg<SMEM>(G, s1 - 1).len;
         const int h = (s1 - s0) >> 1;
+#if SOLAROSC_MIRROR_UNROLL_PAR
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int par = 0; par < 2; ++par) {
             const double* t = par ? t1 : t0;
             State p, x;
@@ -283,8 +299,13 @@ __device__ __forceinline__ void osc_stage(const DevTables& T, const SegTables G,
     SOLAROSC_PH(1);
     // ---- phase 1a: one eigen-system per (fine energy, layer)  (osc.jl:466-470, 370-388) --------
     // two entries per thread and pass: make_entry is branch-free, so the two dependency chains interleave
+#if SOLAROSC_EIG_NODUP
+    for (int t = 2 * threadIdx.x; t < ne * nl; t += 2 * blockDim.x) {   // entries 2t, 2t + 1: every entry computed once
+        const int tb = min(t + 1, ne * nl - 1);
+#else
     for (int t = threadIdx.x; t < ne * nl; t += 2 * blockDim.x) {
         const int tb = min(t + (int)blockDim.x, ne * nl - 1);   // a thread without a second entry repeats the last one
+#endif
         const int ka = t / ne, ela = t - ka * ne, kb = tb / ne, elb = tb - kb * ne;
         const double ea = T.e_calc[2 * i0 + ela], eb = T.e_calc[2 * i0 + elb];
         const double na = T.earth_unc ? p[SOLAROSC_N_FIXED_PARAMS + ka] : 1.0;
@@ -528,7 +549,10 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // ES component uses norm_1).  No barriers inside.
 template <int MODE>
 __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetector& D, const double* __restrict__ p, size_t b,
-                                             double* scr, const RatesOut& O) {
+                                             double* scr, const RatesOut& O, int tid = -1, int nthr = 0) {
+    // (tid, nthr): the threads that share the work -- all of the CTA by default; the fused kernel hands it to the warps that
+    // have no eigen entries to compute
+    if (tid < 0) { tid = threadIdx.x; nthr = blockDim.x; }
     const int nT = T.n_etrue, kt = fold_kt(nT);
     const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
     const double f8 = p[3], fh = p[4];
@@ -540,7 +564,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
     double* bgs_cc = bgs_es + 8 * nte;
     // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
     //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
-    for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
+    for (int i = tid; i < 4 * kt; i += nthr) {
         double sh = 0.0;
         if (i < nT) {
             const double l = D.log_e_norm[i];
@@ -548,7 +572,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
         }
         scale[i] = f8 * sh; scale[4 * kt + i] = fh * sh;
     }
-    for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
+    for (int j = tid; j < 8 * (nte + ntc); j += nthr) {
         double acc = 0.0, c = 0.0;
         if (j < 8 * nte) {
             if (j < D.n_es) {
@@ -1000,7 +1024,9 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
     double* phs = p8s + (size_t)nrow * ldp;
     double* scr = phs + (size_t)nrow * ldp;
     const SegTables G = stage_seg_tables(T, scr + fold_scratch_doubles(nT, L.max_ereco), true);   // the host only launches this kernel when they fit
+    SOLAROSC_PH(10);
     fold_zero_padding(p8s, nT, nrow, ldp);
+    SOLAROSC_PH(11);
     const int n_osc = L.n_points / L.group;
     for (int g = blockIdx.x; g < n_osc; g += gridDim.x) {
         const double* po = params + (size_t)g * L.group * L.param_stride;
@@ -1010,6 +1036,7 @@ llh_kernel(const DevTables T, const RatesLaunch L, const double* __restrict__ pa
         if (MODE != kModeLlh && g != (int)blockIdx.x) __syncthreads();
         const int d0 = L.det_only >= 0 ? L.det_only : 0;
         fold_vectors<MODE>(T, T.det[d0], po, (size_t)g * L.group, scr, O);
+        SOLAROSC_PH(12);
         for (int i0 = 0; i0 < nT; i0 += cbs) {
             // the table of the previous chunk is still being read by slower warps; the previous point's fold is
             // done with the probability tile once its closing barrier has been passed

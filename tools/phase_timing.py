@@ -38,6 +38,11 @@ def main():
     d = np.diff(a[:, :10], axis=1)
     tot = (a[:, 9] - a[:, 0]).mean()
     print(f"{len(a)} CTAs, mean cycles per CTA {tot:.0f}")
+    pro = a[:, [0, 10, 11, 12, 1]]
+    if np.all(pro[:, 1] > 0):
+        dp = np.diff(pro, axis=1)
+        for nm, col in zip(("  prologue: path tables to smem", "  prologue: zero padding", "  prologue: fold vectors (thread 0)", "  prologue: parameters + mixing"), dp.T):
+            print(f"{nm:36s} {col.mean():9.0f}   (p10 {np.percentile(col, 10):.0f}, p90 {np.percentile(col, 90):.0f})")
     for i, nm in enumerate(NAMES):
         print(f"  {nm:32s} {d[:, i].mean():9.0f}  {100 * d[:, i].mean() / tot:5.1f}%   (p10 {np.percentile(d[:, i], 10):.0f}, p90 {np.percentile(d[:, i], 90):.0f})")
 
