@@ -640,7 +640,11 @@ void launch_osc(solarosc_handle* h, const double* d_params, int n_osc, int point
     // energy axis so that about two CTAs per SM exist; never more than shared memory holds
     const size_t per_cb = osc_smem_bytes(T.n_ltbl, 1);
     const int cb_max = (int)std::max<size_t>(1, h->osc_smem_limit / per_cb);
-    int want_chunks = (2 * h->sm_count + n_osc - 1) / n_osc;
+    // (binnings beyond 256 true-energy bins -- the dense convergence grids, a few dozen points per call -- get eight CTAs per SM
+    // instead of two: their CTAs are long, and the tail of the last wave costs more than the extra table set-ups)
+    static const int ctas_env = std::getenv("SOLAROSC_OSC_CTAS_PER_SM") ? atoi(std::getenv("SOLAROSC_OSC_CTAS_PER_SM")) : 0;   // tuning switch
+    const int per_sm = ctas_env > 0 ? ctas_env : (T.n_etrue > 256 ? 8 : 2);
+    int want_chunks = (per_sm * h->sm_count + n_osc - 1) / n_osc;
     want_chunks = std::max(1, std::min(want_chunks, std::max(1, T.n_etrue / 4)));
     int cb = (T.n_etrue + want_chunks - 1) / want_chunks;
     cb = std::max(1, std::min(cb, cb_max));

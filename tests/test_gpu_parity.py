@@ -282,6 +282,20 @@ def test_parameter_corners(engine, coracle, tables):
         assert np.max(np.abs(r[k] - rr[k]) / scale) < 1e-9, k
 
 
+def test_mirrored_walk_equals_the_generic_walk_on_the_device(tables, asimov, draw, monkeypatch):
+    """SOLAROSC_NO_MIRROR makes solarosc_create flag no path as mirrored: every chord then takes the generic step-by-step
+    loop.  P1e of the two walks agrees to rounding (a few 1e-16), lnL to the Poisson sum's noise."""
+    from dune_solaroscfitter_b200.engine import SolarOscEngine
+    p = draw(tables, 600, seed=41, wide=True)
+    with SolarOscEngine(tables, data=asimov) as e:
+        a_p1e, a_lnl, a_small = e.eval_p1e(p[:8]), e.eval_llh(p), e.eval_llh(p[:8])
+    monkeypatch.setenv("SOLAROSC_NO_MIRROR", "1")
+    with SolarOscEngine(tables, data=asimov) as e:
+        b_p1e, b_lnl, b_small = e.eval_p1e(p[:8]), e.eval_llh(p), e.eval_llh(p[:8])
+    assert np.max(np.abs(a_p1e - b_p1e)) < 5e-15 and not np.array_equal(a_p1e, b_p1e)    # (two different instruction streams)
+    assert np.max(np.abs(2 * a_lnl - 2 * b_lnl)) < 1e-7 and np.max(np.abs(2 * a_small - 2 * b_small)) < 1e-7
+
+
 @pytest.mark.parametrize("factor", [10.0, 100.0])
 def test_exposure_scaled_parity(tables, draw, factor):
     """The rounding error of -2lnL grows with the counts per bin: the reference forms m (log m - log e) from two rounded
