@@ -549,10 +549,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // ES component uses norm_1).  No barriers inside.
 template <int MODE>
 __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetector& D, const double* __restrict__ p, size_t b,
-                                             double* scr, const RatesOut& O, int tid = -1, int nthr = 0) {
-    // (tid, nthr): the threads that share the work -- all of the CTA by default; the fused kernel hands it to the warps that
-    // have no eigen entries to compute
-    if (tid < 0) { tid = threadIdx.x; nthr = blockDim.x; }
+                                             double* scr, const RatesOut& O) {
     const int nT = T.n_etrue, kt = fold_kt(nT);
     const int nte = (D.n_es + 7) / 8, ntc = (D.n_cc + 7) / 8;
     const double f8 = p[3], fh = p[4];
@@ -564,7 +561,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
     double* bgs_cc = bgs_es + 8 * nte;
     // ---- per-point vectors: CC cross-section shape (propagation_osc.jl:185-196), backgrounds
     //      (propagation_bg.jl:36-83; every ES component uses norm_1) ----------------------------------
-    for (int i = tid; i < 4 * kt; i += nthr) {
+    for (int i = threadIdx.x; i < 4 * kt; i += blockDim.x) {
         double sh = 0.0;
         if (i < nT) {
             const double l = D.log_e_norm[i];
@@ -572,7 +569,7 @@ __device__ __forceinline__ void fold_vectors(const DevTables& T, const DevDetect
         }
         scale[i] = f8 * sh; scale[4 * kt + i] = fh * sh;
     }
-    for (int j = tid; j < 8 * (nte + ntc); j += nthr) {
+    for (int j = threadIdx.x; j < 8 * (nte + ntc); j += blockDim.x) {
         double acc = 0.0, c = 0.0;
         if (j < 8 * nte) {
             if (j < D.n_es) {
