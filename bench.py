@@ -360,11 +360,13 @@ def main():
     h_np = h_params.numpy()
     out_np = h_lnl.numpy()
 
-    out_all = np.empty(n_total) if world > 1 else None
+    # every rank receives the results of ALL ranks: pinned, caller-owned arrays handed to the library
+    out_all = torch.empty(n_total, dtype=torch.float64).pin_memory().numpy() if world > 1 else None
+    fl_all = torch.empty(n_total, dtype=torch.int32).pin_memory().numpy().view(np.uint32) if world > 1 else None
 
     def step_e2e():
         if world > 1:   # host rows in, all ranks' lnL out: H2D + kernels + NCCL gather + D2H inside the call
-            out_all[:] = eng.eval_llh_sharded(h_np, n_total)
+            eng.eval_llh_sharded(h_np, n_total, out=out_all, flags_out=fl_all)
         else:
             eng.eval_llh(h_np, out=out_np)     # H2D of the step's inputs + kernels + D2H of lnL, all inside
 

@@ -8,6 +8,7 @@
 // the library links against the CUDA runtime only and loads where NCCL is absent.  Included into solarosc_b200.cu.
 #pragma once
 #include <dlfcn.h>
+#include <memory>
 #include <nccl.h>
 
 namespace {
@@ -107,8 +108,10 @@ void comm_reserve(solarosc_handle* h, size_t width) {
 }
 
 // device-resident core: this rank's slice is evaluated into the send buffers, gathered, unpadded into d_lnl_all [n_total]
+// h_params_local != nullptr: the rows are still on the host; chunk c + 1 is copied into d_params_local on the handle's copy
+// stream while the kernels of chunk c run (the caller's buffer is read asynchronously when it is pinned)
 void eval_sharded_device(solarosc_handle* h, const double* d_params_local, size_t n_total, size_t group, double* d_lnl_all,
-                         uint32_t* d_flags_all, cudaStream_t st) {
+                         uint32_t* d_flags_all, cudaStream_t st, const double* h_params_local = nullptr) {
     solarosc_comm_state* c = h->comm;
     size_t lo, hi;
     shard_bounds(n_total, group, c->rank, c->world, &lo, &hi);
@@ -122,6 +125,12 @@ void eval_sharded_device(solarosc_handle* h, const double* d_params_local, size_
     h->tev_stream = st;
     for (size_t b0 = 0; b0 < n_local; b0 += step) {
         const int nb = (int)std::min(step, n_local - b0);
+        if (h_params_local) {
+            CK(cudaMemcpyAsync(const_cast<double*>(d_params_local) + b0 * h->P, h_params_local + b0 * h->P, (size_t)nb * h->P * sizeof(double),
+                               cudaMemcpyHostToDevice, h->s_in));
+            CK(cudaEventRecord(h->ev_in[0], h->s_in));
+            CK(cudaStreamWaitEvent(st, h->ev_in[0], 0));
+        }
         RatesOut O{};
         O.lnl = c->d_send + b0; O.flags = c->d_fsend + b0;
         if (h->timing) CK(cudaEventRecord(h->next_tev(), st));
@@ -238,15 +247,18 @@ int solarosc_eval_llh_sharded(solarosc_handle* h, const double* params_local, si
         double* d_l = d_p + n_local * h->P;
         uint32_t* d_f = reinterpret_cast<uint32_t*>(d_l + n_total);
         h->launches = 0;
-        if (n_local) CK(cudaMemcpyAsync(d_p, params_local, n_local * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        eval_sharded_device(h, d_p, n_total, group, d_l, d_f, h->stream);
+        CK(cudaStreamSynchronize(h->stream));   // (the scratch may just have been reallocated; nothing of an earlier call is in flight)
+        eval_sharded_device(h, d_p, n_total, group, d_l, d_f, h->stream, params_local);
         CK(cudaMemcpyAsync(out_lnl, d_l, n_total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        std::vector<uint32_t> fl(n_total);
-        CK(cudaMemcpyAsync(fl.data(), d_f, n_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        // flags straight into the caller's array when there is one (no temporary, no second copy: with 8 ranks every rank
+        // receives 12 bytes for each of the n_total points)
+        std::unique_ptr<uint32_t[]> tmp;
+        uint32_t* fl = out_flags;
+        if (!fl) { tmp.reset(new uint32_t[n_total]); fl = tmp.get(); }
+        CK(cudaMemcpyAsync(fl, d_f, n_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         bool neg = false;
         for (size_t i = 0; i < n_total; ++i) neg |= (fl[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
-        if (out_flags) std::memcpy(out_flags, fl.data(), n_total * sizeof(uint32_t));
         if (neg) {
             h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
             return (int)SOLAROSC_ERR_NEGATIVE_RATE;

@@ -276,10 +276,15 @@ class SolarOscEngine:
                                                   self.world if world is None else world, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
-    def eval_llh_sharded(self, params_local, n_total: int, group: int = 1, return_flags: bool = False):
-        """This rank's rows in, lnL of all n_total points out (all-gathered over NCCL inside the library)."""
+    def eval_llh_sharded(self, params_local, n_total: int, group: int = 1, return_flags: bool = False, out=None, flags_out=None):
+        """This rank's rows in, lnL of all n_total points out (all-gathered over NCCL inside the library).  `out` /
+        `flags_out`: caller-owned result arrays (float64 / uint32, n_total entries; pinned memory makes the copy back
+        asynchronous), allocated here when absent."""
         p = self._params(params_local) if len(params_local) else np.empty((0, self.n_params))
-        out, fl = np.empty(n_total), np.zeros(n_total, dtype=np.uint32)
+        out = np.empty(n_total) if out is None else out
+        fl = np.empty(n_total, dtype=np.uint32) if flags_out is None else flags_out
+        if out.shape != (n_total,) or out.dtype != np.float64 or fl.shape != (n_total,) or fl.dtype != np.uint32:
+            raise ValueError("out / flags_out must be float64 / uint32 arrays of n_total entries")
         st = self._L.solarosc_eval_llh_sharded(self._h, _dp(p), n_total, group, _dp(out), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
         if st != abi.ERR_NEGATIVE_RATE:
             self._check(st)
