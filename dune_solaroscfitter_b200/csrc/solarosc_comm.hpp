@@ -68,9 +68,23 @@ void shard_bounds(size_t n_total, size_t group, int rank, int world, size_t* lo,
 }
 
 // gathered[world][width] (padded slices) -> out[n_total]
+// (any_flags, when given, receives the OR of all flags: the host then knows about a negative-rate error without walking
+// n_total words)
 __global__ void unpad_gather_kernel(const double* __restrict__ g_lnl, const uint32_t* __restrict__ g_fl, size_t width, size_t n_total,
-                                    size_t group, int world, double* __restrict__ out_lnl, uint32_t* __restrict__ out_fl) {
+                                    size_t group, int world, double* __restrict__ out_lnl, uint32_t* __restrict__ out_fl,
+                                    uint32_t* __restrict__ any_flags) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (any_flags) {
+        uint32_t f = 0;
+        if (i < n_total) {
+            const size_t n_groups = n_total / group, base = n_groups / world, extra = n_groups % world, gi = i / group;
+            const size_t cut = extra * (base + 1);
+            const size_t r = gi < cut ? gi / (base + 1) : extra + (base ? (gi - cut) / base : 0);
+            f = g_fl[r * width + (i - (r * base + (r < extra ? r : extra)) * group)];
+        }
+        f = __reduce_or_sync(0xffffffffu, f);
+        if ((threadIdx.x & 31) == 0 && f) atomicOr(any_flags, f);
+    }
     if (i >= n_total) return;
     const size_t n_groups = n_total / group, base = n_groups / world, extra = n_groups % world;
     const size_t gi = i / group;
@@ -111,7 +125,7 @@ void comm_reserve(solarosc_handle* h, size_t width) {
 // h_params_local != nullptr: the rows are still on the host; chunk c + 1 is copied into d_params_local on the handle's copy
 // stream while the kernels of chunk c run (the caller's buffer is read asynchronously when it is pinned)
 void eval_sharded_device(solarosc_handle* h, const double* d_params_local, size_t n_total, size_t group, double* d_lnl_all,
-                         uint32_t* d_flags_all, cudaStream_t st, const double* h_params_local = nullptr) {
+                         uint32_t* d_flags_all, cudaStream_t st, const double* h_params_local = nullptr, uint32_t* d_any = nullptr) {
     solarosc_comm_state* c = h->comm;
     size_t lo, hi;
     shard_bounds(n_total, group, c->rank, c->world, &lo, &hi);
@@ -142,8 +156,9 @@ void eval_sharded_device(solarosc_handle* h, const double* d_params_local, size_
     NCK(nccl_api().AllGather(c->d_send, c->d_recv, width, ncclDouble, c->comm, st));
     NCK(nccl_api().AllGather(c->d_fsend, c->d_frecv, width, ncclUint32, c->comm, st));
     NCK(nccl_api().GroupEnd());
+    if (d_any) CK(cudaMemsetAsync(d_any, 0, sizeof(uint32_t), st));
     unpad_gather_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(c->d_recv, c->d_frecv, width, n_total, group, c->world, d_lnl_all,
-                                                                           d_flags_all);
+                                                                           d_flags_all, d_any);
     CK(cudaGetLastError());
     ++h->launches;
 }
@@ -242,23 +257,22 @@ int solarosc_eval_llh_sharded(solarosc_handle* h, const double* params_local, si
         REQUIRE(hi == lo || params_local, "params_local must not be NULL");
         // this rank's rows to the device, the gathered vectors back: [params | lnl | flags] in the scratch
         const size_t n_local = hi - lo;
-        h->ensure_scratch((n_local * h->P + n_total) * sizeof(double) + n_total * sizeof(uint32_t));
+        h->ensure_scratch((n_local * h->P + n_total) * sizeof(double) + (n_total + 2) * sizeof(uint32_t));
         double* d_p = h->d_scratch;
         double* d_l = d_p + n_local * h->P;
         uint32_t* d_f = reinterpret_cast<uint32_t*>(d_l + n_total);
+        uint32_t* d_any = d_f + n_total;
         h->launches = 0;
         CK(cudaStreamSynchronize(h->stream));   // (the scratch may just have been reallocated; nothing of an earlier call is in flight)
-        eval_sharded_device(h, d_p, n_total, group, d_l, d_f, h->stream, params_local);
+        eval_sharded_device(h, d_p, n_total, group, d_l, d_f, h->stream, params_local, d_any);
         CK(cudaMemcpyAsync(out_lnl, d_l, n_total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        // flags straight into the caller's array when there is one (no temporary, no second copy: with 8 ranks every rank
-        // receives 12 bytes for each of the n_total points)
-        std::unique_ptr<uint32_t[]> tmp;
-        uint32_t* fl = out_flags;
-        if (!fl) { tmp.reset(new uint32_t[n_total]); fl = tmp.get(); }
-        CK(cudaMemcpyAsync(fl, d_f, n_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        // flags straight into the caller's array when it wants them; whether any point carries a negative-rate error comes back
+        // as one word (with 8 ranks every rank receives 12 bytes for each of the n_total points: no host pass over them)
+        if (out_flags) CK(cudaMemcpyAsync(out_flags, d_f, n_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        uint32_t any = 0;
+        CK(cudaMemcpyAsync(&any, d_any, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        bool neg = false;
-        for (size_t i = 0; i < n_total; ++i) neg |= (fl[i] & SOLAROSC_FLAG_NEG_ERROR) != 0;
+        const bool neg = (any & SOLAROSC_FLAG_NEG_ERROR) != 0;
         if (neg) {
             h->err = "an expected rate was <= -1e-3 for at least one point (lnL = NaN there)";
             return (int)SOLAROSC_ERR_NEGATIVE_RATE;

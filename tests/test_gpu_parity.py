@@ -334,8 +334,10 @@ def test_exposure_scaled_parity(tables, draw, factor):
 def test_single_rank_communicator_gathers_the_same_values(tables, asimov, draw):
     """The in-library NCCL path with a one-rank communicator: solarosc_eval_llh_sharded == solarosc_eval_llh (the
     multi-rank run is tools/sharded_check.py under torchrun)."""
+    import ctypes as C
+    from dune_solaroscfitter_b200 import abi
     from dune_solaroscfitter_b200.engine import SolarOscEngine
-    p = draw(tables, 27 * 40, seed=91)
+    p = np.ascontiguousarray(draw(tables, 27 * 40, seed=91))
     p[5, 9] = 2.5
     with SolarOscEngine(tables, data=asimov) as e:
         e.comm_init(e.comm_unique_id(), 0, 1)
@@ -344,4 +346,14 @@ def test_single_rank_communicator_gathers_the_same_values(tables, asimov, draw):
         b, fb = e.eval_llh(p, return_flags=True)
         g = e.eval_llh_sharded(p, len(p), group=27)
         gb = e.eval_llh(p, group=27)
+        # a negative-rate error anywhere in the gathered batch comes back as the call's status (one word OR-ed on the
+        # device), caller-owned result arrays
+        q = p.copy(); q[700, -5:] = -2.2e-6
+        out, fl = np.empty(len(q)), np.empty(len(q), dtype=np.uint32)
+        st = e._L.solarosc_eval_llh_sharded(e._h, q.ctypes.data_as(C.POINTER(C.c_double)), len(q), 1,
+                                            out.ctypes.data_as(C.POINTER(C.c_double)), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert st == abi.ERR_NEGATIVE_RATE and np.isnan(out[700]) and fl[700] & abi.FLAG_NEG_ERROR
+        assert e._L.solarosc_eval_llh_sharded(e._h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), 1,
+                                              out.ctypes.data_as(C.POINTER(C.c_double)), None) == abi.OK
+        assert np.array_equal(out, b)
     assert np.array_equal(a, b) and np.array_equal(fa, fb) and np.array_equal(g, gb)
