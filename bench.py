@@ -362,11 +362,10 @@ def main():
 
     # every rank receives the results of ALL ranks: pinned, caller-owned arrays handed to the library
     out_all = torch.empty(n_total, dtype=torch.float64).pin_memory().numpy() if world > 1 else None
-    fl_all = torch.empty(n_total, dtype=torch.int32).pin_memory().numpy().view(np.uint32) if world > 1 else None
 
     def step_e2e():
         if world > 1:   # host rows in, all ranks' lnL out: H2D + kernels + NCCL gather + D2H inside the call
-            eng.eval_llh_sharded(h_np, n_total, out=out_all, flags_out=fl_all)
+            eng.eval_llh_sharded(h_np, n_total, out=out_all)   # lnL of all ranks; a negative-rate error would come back as the status
         else:
             eng.eval_llh(h_np, out=out_np)     # H2D of the step's inputs + kernels + D2H of lnL, all inside
 
@@ -517,7 +516,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.grid, n_cell, n if world > 1 else len(params), P, world, args.scaling),
         "roofline": roofline, "roofline_rates": roofline_rates,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * P * 8), "d2h_bytes_per_step": int((n_total if world > 1 else n) * 12)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * P * 8), "d2h_bytes_per_step": int(n_total * 8 if world > 1 else n * 12)},
         "grouped": {"value": grouped_value, "unit": UNIT, "group": n_cell,
                     "note": "oscillation stage shared by the points of a scan cell (precomputed_osc); not the headline"},
         "value_and_gradient": {"value": grad_value, "unit": "lnL + gradient evaluations/s", "batch": 4096,

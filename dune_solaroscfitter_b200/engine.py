@@ -282,10 +282,11 @@ class SolarOscEngine:
         asynchronous), allocated here when absent."""
         p = self._params(params_local) if len(params_local) else np.empty((0, self.n_params))
         out = np.empty(n_total) if out is None else out
-        fl = np.empty(n_total, dtype=np.uint32) if flags_out is None else flags_out
-        if out.shape != (n_total,) or out.dtype != np.float64 or fl.shape != (n_total,) or fl.dtype != np.uint32:
+        fl = flags_out if flags_out is not None else (np.empty(n_total, dtype=np.uint32) if return_flags else None)   # None: not copied back
+        if out.shape != (n_total,) or out.dtype != np.float64 or (fl is not None and (fl.shape != (n_total,) or fl.dtype != np.uint32)):
             raise ValueError("out / flags_out must be float64 / uint32 arrays of n_total entries")
-        st = self._L.solarosc_eval_llh_sharded(self._h, _dp(p), n_total, group, _dp(out), fl.ctypes.data_as(C.POINTER(C.c_uint32)))
+        st = self._L.solarosc_eval_llh_sharded(self._h, _dp(p), n_total, group, _dp(out),
+                                               fl.ctypes.data_as(C.POINTER(C.c_uint32)) if fl is not None else None)
         if st != abi.ERR_NEGATIVE_RATE:
             self._check(st)
         return (out, fl) if return_flags else out
