@@ -888,8 +888,9 @@ int eval_llh_small(solarosc_handle* h, const double* params, size_t n, size_t gr
     if (!h->small_graph || h->small_n != n || h->small_group != group) {
         if (h->small_graph) { cudaGraphExecDestroy(h->small_graph); h->small_graph = nullptr; }
         cudaGraph_t g = nullptr;
-        if (n / group >= (size_t)h->sm_count) pipe_plan(h, kModeLlh, (int)group, -1);   // uploads its tables: not inside a capture
-        else h->osc();                                                                  // (nor the workspace allocation)
+        // nothing may allocate inside the capture: the pipe plan uploads its tables, the stage-separated path its workspace
+        if (n / group >= (size_t)h->sm_count) pipe_plan(h, kModeLlh, (int)group, -1);
+        if (n / group < (size_t)h->sm_count || !h->fused_ok || !h->use_fused) h->osc();
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         try {
             CK(cudaMemcpyAsync(h->d_params2[0], h->h_params_pin, n * h->P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
