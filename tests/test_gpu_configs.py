@@ -90,6 +90,9 @@ def test_c4_dense_200x200_matches_oracle():
         perbin = e.eval_perbin(p[:1])
         big = _earth_draws(t, 300, 6)                                  # more points than SMs
         lnl_big = e.eval_llh(big)
+    with SolarOscEngine(t, data=data) as e2:                           # a fresh handle whose FIRST call is a graph-replayed small
+        lnl_200 = e2.eval_llh(big[:200])                               # batch of more points than SMs (workspace allocated before the capture)
+    assert np.array_equal(lnl_200, lnl_big[:200])
     assert p1e.shape == (3, 200, 200)
     assert np.max(np.abs(p1e - ref_p1e)) < 5e-12
     assert np.max(np.abs(osc["nue_8B_night"] - ref_osc[:, 0, 1:])) < 5e-12
